@@ -1,0 +1,190 @@
+/*
+ * lrbinner_b200.h — C ABI of the B200-native LRBinner profile stage (liblrb200.so).
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  All functions return 0 on success and a
+ * non-zero LRB_E* code on failure; lrb_last_error() gives the message of the calling thread's last
+ * failure.  The library is thread-compatible (one context per thread), not thread-safe.
+ *
+ * Reference interfaces replaced (paths relative to the LRBinner repository):
+ *   lrb_count_kmers    <- `count-kmers <in> <out> <k> <threads>`        mbcclr_utils/count-kmers.cpp:189-218
+ *                         launched by run_kmers()                       mbcclr_utils/runners_utils.py:78-85
+ *   lrb_count_15mers   <- `count-15mers <in> <out> <threads>`           mbcclr_utils/count-15mers.cpp:97-123
+ *                         launched by run_15mer_counts()                mbcclr_utils/runners_utils.py:88-95
+ *   lrb_search_15mers  <- `search-15mers <tbl> <in> <out> <bs> <bc> <t>` mbcclr_utils/search-15mers.cpp:121-157
+ *                         launched by run_15mer_vecs()                  mbcclr_utils/runners_utils.py:98-105
+ *   lrb_profile        <- the three calls above fused (stages 1_1,1_2,2_1, mbcclr_utils/pipelines.py:269-306)
+ *   lrb_reads_*        <- SeqReader / kseq_read                         mbcclr_utils/io_utils.h:133-165, kseq.h:177-218
+ *   lrb_dev_composition<- count_kmers()                                 mbcclr_utils/count-kmers.cpp:66-95
+ *   lrb_dev_count      <- line_to_kmer_counts()                         mbcclr_utils/kmer_utils.h:114-156
+ *   lrb_dev_search     <- line_to_vec()                                 mbcclr_utils/kmer_utils.h:24-87
+ *   lrb_table_*        <- writeKmerFile / readKmerFile                  mbcclr_utils/kmer_utils.h:89-112
+ *   lrb_format_*       <- std::to_string(double) row emitters           count-kmers.cpp:110-118, search-15mers.cpp:35-48
+ */
+#ifndef LRBINNER_B200_H
+#define LRBINNER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRB_OK 0
+#define LRB_EINVAL 1   /* bad argument */
+#define LRB_EIO 2      /* file could not be opened / written */
+#define LRB_ECUDA 3    /* CUDA runtime error (also: no device) */
+#define LRB_ENOMEM 4
+#define LRB_EFORMAT 5  /* malformed table file */
+
+#define LRB_TABLE_ENTRIES (1ull << 30) /* 4^15, count-15mers.cpp:99 */
+#define LRB_TILE_BLOCKS 256            /* 32-slot blocks of one read per warp tile */
+#define LRB_MAX_BINS 4096              /* coverage histogram width accepted by lrb_dev_search */
+
+int lrb_version(void);
+const char* lrb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed read set (host side).  Layout: DESIGN.md "Data layout in HBM" / csrc/lane_core.cuh.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lrb_reads lrb_reads;
+
+typedef struct {
+    uint64_t n_reads;      /* N */
+    uint64_t n_blocks;     /* 32-slot blocks in the stream */
+    uint64_t n_tiles;      /* warp tiles (<= LRB_TILE_BLOCKS blocks of one read each) */
+    uint64_t total_bases;  /* L = sum of read lengths */
+    const uint32_t* codes;     /* 2*n_blocks + 2 words, 2-bit codes, first slot in the top bit pair */
+    const uint32_t* valid;     /* n_blocks + 1 words, bit s = slot s is an in-read uppercase ACGT */
+    const uint32_t* read_len;  /* N */
+    const uint32_t* read_blk;  /* N+1: first block of read r; read r owns floor(len/32)+1 blocks */
+    const uint32_t* tile_read; /* n_tiles */
+    const uint32_t* tile_blk;  /* n_tiles: first (global) block of the tile */
+} lrb_reads_view;
+
+/* Parse FASTA/FASTQ, plain or gzip, with the record semantics of kseq_read as used by SeqReader
+ * (multi-line records, CR stripping, '>'/'@'/'+' leading a line ends the sequence, a bad FASTQ record
+ * ends the stream silently, sequence cut at the first NUL).  A missing/unreadable file yields an EMPTY
+ * read set and LRB_OK, like the tools.  `threads` parallelises the 2-bit packing. */
+int lrb_reads_from_file(const char* path, int threads, lrb_reads** out);
+/* Concatenated ASCII bases + offsets[n_reads+1] (read r = bases[offsets[r], offsets[r+1])). */
+int lrb_reads_from_ascii(const char* bases, const uint64_t* offsets, uint64_t n_reads, int threads, lrb_reads** out);
+/* Layout only (no bases): builds read_blk / tile arrays for given lengths and allocates zeroed
+ * codes/valid — used when the stream is produced on the device (synthetic generator). */
+int lrb_reads_from_lengths(const uint32_t* lengths, uint64_t n_reads, lrb_reads** out);
+int lrb_reads_view_get(const lrb_reads* r, lrb_reads_view* view);  /* host pointers */
+/* Copy read i back out as ASCII from the packed form ('A','C','T','G' by code; lossy for non-ACGT). */
+int lrb_reads_unpack(const lrb_reads* r, uint64_t i, char* dst, uint64_t cap);
+void lrb_reads_free(lrb_reads* r);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-pointer level (the kernels).  All pointers are DEVICE pointers; `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).  Calls are asynchronous on that stream.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* count_kmers (count-kmers.cpp:66-95): counts[N*P] += raw canonical k-mer counts, P = 32/136/512 for
+ * k = 3/4/5.  counts must be zeroed by the caller (the call accumulates). EVERY byte of a read takes part
+ * (no ACGT check), total windows per read = max(0, len-k+1). Restricted to reads [read_lo, read_hi). */
+int lrb_dev_composition(const lrb_reads_view* dev, int k, uint32_t* counts, uint64_t tile_lo, uint64_t tile_hi,
+                        void* stream);
+
+/* line_to_kmer_counts (kmer_utils.h:114-156) over blocks [blk_lo, blk_hi): for every valid 15-mer
+ * window increments table[c] where c is the member of {val, revcomp(val)} with bit 15 clear, if
+ * key_lo <= c < key_hi (key-space shard; pass 0, 2^30 for everything).  lrb_dev_mirror then makes
+ * table[x] = table[revcomp(x)] for every x with bit 15 set in [0, 2^30), which yields exactly the
+ * reference table (both strands incremented per window => T[x] == T[rc(x)]).  u32 wrap-around. */
+int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_t blk_lo, uint64_t blk_hi,
+                  uint32_t key_lo, uint32_t key_hi, void* stream);
+int lrb_dev_mirror(uint32_t* table, void* stream);
+
+/* line_to_vec (kmer_utils.h:24-87): hist[N*bins] += bucket counts, sums[N] += valid windows, for the
+ * reads of tiles [tile_lo, tile_hi).  Looks up table[val] (forward key) — table must be mirrored —
+ * restricted to windows whose canonical key lies in [key_lo, key_hi) (pass 0, 2^30 for all).
+ * hist/sums must be zeroed by the caller. */
+int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_size, int bins, uint32_t* hist,
+                   uint32_t* sums, uint64_t tile_lo, uint64_t tile_hi, uint32_t key_lo, uint32_t key_hi, void* stream);
+
+/* Pack ASCII on the device: bases[] (device, concatenated) -> codes/valid of `dev` (layout prebuilt). */
+int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, const uint64_t* offsets, void* stream);
+
+/* Text epilogue on the device: fixed-width "%f" rows, byte-identical to the tools' output.
+ *   composition: N rows of P values "d.dddddd " then '\n'            (count-kmers.cpp:110-118)
+ *   coverage   : N rows of B values separated by ' ', then '\n'      (search-15mers.cpp:35-48)
+ * value = count/max(1,total) resp. count/sum with the <1e-4 -> 0 rule (kmer_utils.h:75-84). */
+int lrb_dev_format_composition(const uint32_t* counts, const uint32_t* read_len, uint64_t n_reads, int k, char* text,
+                               void* stream);
+int lrb_dev_format_coverage(const uint32_t* hist, const uint32_t* sums, uint64_t n_reads, int bins, char* text,
+                            void* stream);
+
+/* Synthetic ONT/HiFi-like reads generated directly into the packed stream (bench/test input only).
+ * meta[4*r+0..3] = genome id, start, flags (bit0 reverse strand, bit1 lowercase read), reserved.
+ * genome g has glen[g] bases, base i = hash(seed,g,i).  thresholds are u32 fractions of 2^32. */
+typedef struct {
+    uint64_t seed;
+    uint32_t n_genomes;
+    uint32_t sub_thr, ins_thr, del_thr, n_thr;
+} lrb_synth_params;
+int lrb_dev_synth(const lrb_reads_view* dev, const lrb_synth_params* p, const uint32_t* glen, const uint32_t* meta,
+                  void* stream);
+/* The same generator on the host, writing ASCII (tests feed this to the oracle). */
+int lrb_synth_host(const lrb_synth_params* p, const uint32_t* glen, const uint32_t* meta, const uint32_t* lengths,
+                   uint64_t n_reads, const uint64_t* offsets, char* bases);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer level: owns device memory, streams and the H2D/D2H pipeline on one GPU.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct lrb_ctx lrb_ctx;
+int lrb_ctx_create(int device, lrb_ctx** out);
+void lrb_ctx_destroy(lrb_ctx* ctx);
+
+/* Whole profile stage for one read set held in (pinned) HOST memory:
+ *   H2D(packed reads) -> composition -> 15-mer count -> mirror -> search -> D2H(results).
+ * comp_counts[N*P] (P from k), cov_hist[N*bins], cov_sums[N] are HOST buffers (may be NULL to skip the
+ * corresponding phase).  If table_host != NULL the 4 GiB table is copied back as well.
+ * If use_loaded_table != 0 the count phase is skipped and the table already in the context is searched. */
+int lrb_profile_host(lrb_ctx* ctx, const lrb_reads* reads, int k, long bin_size, int bins, uint32_t* comp_counts,
+                     uint32_t* cov_hist, uint32_t* cov_sums, uint32_t* table_host, int use_loaded_table);
+/* Per-phase device milliseconds of the last lrb_profile_host call:
+ * [0] h2d [1] composition [2] memset+count [3] mirror [4] search [5] d2h [6] total */
+int lrb_ctx_last_timings(const lrb_ctx* ctx, float* ms7);
+int lrb_ctx_table_load(lrb_ctx* ctx, const char* path);          /* readKmerFile -> HBM */
+int lrb_ctx_table_save(lrb_ctx* ctx, const char* path);          /* HBM -> writeKmerFile format */
+
+/* ------------------------------------------------------------------------------------------------
+ * Host text / file epilogue (multi-threaded, exact "%f").
+ * ---------------------------------------------------------------------------------------------- */
+/* q = the 6 decimals printf("%f") prints for double(num)/double(den), as an integer in [0, 10^6]
+ * (den == 0 is treated as 1: max(1.0,total), count-kmers.cpp:91).  coverage != 0 applies the
+ * `< 1e-4 -> 0` rule first (kmer_utils.h:80-83). */
+uint32_t lrb_fixed6(uint32_t num, uint32_t den, int coverage);
+int lrb_write_composition_txt(const char* path, const uint32_t* counts, const uint32_t* read_len, uint64_t n_reads,
+                              int k, int threads);
+int lrb_write_coverage_txt(const char* path, const uint32_t* hist, const uint32_t* sums, uint64_t n_reads, int bins,
+                           int threads);
+/* .npy (float64, C order) holding float(text) for every value: what pipelines.py:313-324 would produce. */
+int lrb_write_composition_npy(const char* path, const uint32_t* counts, const uint32_t* read_len, uint64_t n_reads,
+                              int k, int threads);
+int lrb_write_coverage_npy(const char* path, const uint32_t* hist, const uint32_t* sums, uint64_t n_reads, int bins,
+                           int threads);
+int lrb_table_write_file(const char* path, const uint32_t* table);  /* u64 2^30, then 2^30 u32 */
+int lrb_table_read_file(const char* path, uint32_t* table);
+
+/* canonical k-mer index table of count-kmers (compute_kmer_inds, count-kmers.cpp:38-64); returns P. */
+int lrb_kmer_lut(int k, uint16_t* lut /* 4^k */);
+
+/* ------------------------------------------------------------------------------------------------
+ * File level: the drop-ins for the three tools (same argument meaning; exit code -> return value).
+ * ---------------------------------------------------------------------------------------------- */
+int lrb_count_kmers(const char* reads_path, const char* out_txt, int k, int threads);
+int lrb_count_15mers(const char* reads_path, const char* out_table, int threads);
+int lrb_search_15mers(const char* table_path, const char* reads_path, const char* out_txt, long bin_size, int bins,
+                      int threads);
+/* Fused stage: parse once, keep reads + table in HBM, write com_profs, cov_profs (and 15mers-counts if
+ * write_table) into out_dir/profiles/; write_npy additionally emits com_profs.npy / cov_profs.npy. */
+int lrb_profile(const char* reads_path, const char* out_dir, int k, long bin_size, int bins, int threads,
+                int write_table, int write_npy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

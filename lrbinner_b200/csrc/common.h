@@ -1,0 +1,34 @@
+// common.h — error plumbing shared by the translation units of liblrb200.so
+#pragma once
+#include <stdint.h>
+
+#include "../../include/lrbinner_b200.h"
+
+// Records `msg` (printf-style) as the calling thread's last error and returns `code`.
+int lrb_set_error(int code, const char* fmt, ...);
+
+#ifdef __CUDACC__
+#define LRB_CUDA(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t lrb_e_ = (expr);                                                                        \
+        if (lrb_e_ != cudaSuccess)                                                                          \
+            return lrb_set_error(LRB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(lrb_e_),     \
+                                 __FILE__, __LINE__);                                                       \
+    } while (0)
+#endif
+
+// host-side internals shared between ingest.cpp / format.cpp / api.cu
+struct lrb_reads {
+    uint64_t n_reads = 0, n_blocks = 0, n_tiles = 0, total_bases = 0;
+    uint32_t* codes = nullptr;      // 2*n_blocks + 2
+    uint32_t* valid = nullptr;      // n_blocks + 1
+    uint32_t* read_len = nullptr;   // n_reads
+    uint32_t* read_blk = nullptr;   // n_reads + 1
+    uint32_t* tile_read = nullptr;  // n_tiles
+    uint32_t* tile_blk = nullptr;   // n_tiles
+    bool pinned = false;            // buffers came from cudaHostAlloc
+};
+
+// page-locked when a CUDA device is usable, plain aligned memory otherwise (host-only unit tests)
+void* lrb_host_alloc(size_t bytes, bool* pinned);
+void lrb_host_free(void* p, bool pinned);

@@ -1,0 +1,356 @@
+// kernels.cu — sm_100a kernels of the profile stage and their C-ABI launchers (lrb_dev_*).
+//
+// Work decomposition (DESIGN.md "Kernels"):
+//   * composition / search : one WARP per tile (<= 256 blocks of 32 slots of ONE read); lanes take blocks
+//     lane, lane+32, ... so every warp load is a fully coalesced 256 B (codes) / 128 B (validity) line;
+//     per-warp shared-memory histogram (smem atomics, measured ~1.6 T ops/s on B200), flushed to the
+//     read's output row with one RED per non-zero bin.
+//   * count  : one THREAD per block, grid-stride; read-oblivious because padding slots are invalid;
+//     one RED.ADD.U32 per valid window on the bit-15-clear key of {val, rc(val)}.
+//   * mirror : 64x64 tiled "transpose" T[x] = T[rc(x)] for bit-15-set x (coalesced both ways).
+// No tensor cores anywhere: nothing here is a dense contraction (BASELINE.json north_star).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lrbinner_b200.h"
+#include "common.h"
+#include "lane_core.cuh"
+
+using namespace lrb;
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+
+// canonical-index LUTs of count-kmers (compute_kmer_inds), filled once per device by ensure_luts()
+__device__ uint16_t g_lut3[64];
+__device__ uint16_t g_lut4[256];
+__device__ uint16_t g_lut5[1024];
+
+template <int K> struct CompTraits;
+template <> struct CompTraits<3> { static constexpr int P = 32; };
+template <> struct CompTraits<4> { static constexpr int P = 136; };
+template <> struct CompTraits<5> { static constexpr int P = 512; };
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) { return __ldg(p); }
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------------
+// composition: count_kmers (count-kmers.cpp:66-95)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kCtaThreads)
+k_composition(lrb_reads_view R, uint32_t* __restrict__ out, uint64_t tile_lo, uint64_t tile_hi) {
+    constexpr int P = CompTraits<K>::P;
+    constexpr int NK = 1 << (2 * K);
+    __shared__ uint16_t s_lut[NK];
+    __shared__ uint32_t s_hist[kWarpsPerCta][P];
+
+    const uint16_t* glut = (K == 3) ? g_lut3 : (K == 4) ? g_lut4 : g_lut5;
+    for (int i = threadIdx.x; i < NK; i += kCtaThreads) s_lut[i] = glut[i];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* hist = s_hist[warp];
+    for (int i = lane; i < P; i += 32) hist[i] = 0;
+    __syncthreads();
+
+    const uint64_t tile = tile_lo + (uint64_t)blockIdx.x * kWarpsPerCta + warp;
+    if (tile >= tile_hi) return;
+    const uint32_t r = R.tile_read[tile];
+    const uint32_t b0 = R.tile_blk[tile];
+    const uint32_t rb0 = R.read_blk[r], rb1 = R.read_blk[r + 1];
+    const uint32_t len = R.read_len[r];
+    const uint32_t nblk = min((uint32_t)kTileBlocks, rb1 - b0);
+    const uint2* codes2 = reinterpret_cast<const uint2*>(R.codes);
+
+    for (uint32_t i = lane; i < nblk; i += 32) {
+        const uint32_t gb = b0 + i;
+        const uint2 w = ld_stream_u2(codes2 + gb);
+        const uint32_t p0 = (gb - rb0) * 32u;            // read position of slot 0 of this block
+        const uint32_t pw = (p0 != 0) ? ld_stream_u32(R.codes + 2 * (size_t)gb - 1) : 0u;
+        const uint32_t n_in = min(32u, len - p0);        // in-read slots of this block (0..32)
+        uint32_t m = (n_in >= 32u) ? 0xFFFFFFFFu : ((1u << n_in) - 1u);
+        if (p0 == 0) m &= ~((1u << (K - 1)) - 1u);       // first K-1 positions of a read end no window
+        if (m == 0xFFFFFFFFu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(&hist[s_lut[kmer_ending_at<K>(pw, w.x, w.y, j)]], 1u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if ((m >> j) & 1u) atomicAdd(&hist[s_lut[kmer_ending_at<K>(pw, w.x, w.y, j)]], 1u);
+        }
+    }
+    __syncwarp();
+    uint32_t* row = out + (size_t)r * P;
+    for (int i = lane; i < P; i += 32) {
+        const uint32_t c = hist[i];
+        if (c) atomicAdd(row + i, c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 15-mer count: line_to_kmer_counts (kmer_utils.h:114-156), canonical half + later mirror
+// ------------------------------------------------------------------------------------------------
+template <bool FILTER>
+__global__ void __launch_bounds__(256)
+k_count15(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, uint32_t* __restrict__ table,
+          uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi) {
+    const uint2* codes2 = reinterpret_cast<const uint2*>(codes);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t gb = blk_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < blk_hi; gb += stride) {
+        const uint32_t v = ld_stream_u32(valid + gb);
+        const uint32_t pv = gb ? ld_stream_u32(valid + gb - 1) : 0u;
+        const uint32_t m = window15_mask(pv, v);
+        if (m == 0) continue;
+        const uint2 w = ld_stream_u2(codes2 + gb);
+        const uint32_t pw = gb ? ld_stream_u32(codes + 2 * gb - 1) : 0u;
+        const uint32_t r0 = rc16(w.y), r1 = rc16(w.x), r2 = rc16(pw);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if ((m >> j) & 1u) {
+                const uint32_t val = kmer_ending_at<15>(pw, w.x, w.y, j);
+                const uint32_t key = canonical15(val, rc15_ending_at(r0, r1, r2, j));
+                if (!FILTER || (key >= key_lo && key < key_hi)) atomicAdd(table + key, 1u);
+            }
+        }
+    }
+}
+
+// mirror: T[x] = T[rc(x)] for all x with bit 15 set.  x = (H:14 | M:2 | L:14) -> rc(x) = (rc7(L) | M^2 | rc7(H)).
+// CTA tile: H = (a | hrest), L = (lrest | b) with a = top 3 bases of H, b = low 3 bases of L (64 values each).
+// Source rows are indexed by rc3(b) (high bases of the source H) and hold 64 contiguous entries indexed by rc3(a).
+__device__ __forceinline__ uint32_t rc_small(uint32_t x, int nbases) {  // reverse-complement of nbases (<=16) bases
+    return rc16(x << (32 - 2 * nbases)) & ((1u << (2 * nbases)) - 1u);
+}
+
+__global__ void __launch_bounds__(256) k_mirror(uint32_t* __restrict__ table) {
+    __shared__ uint32_t tile[64][65];
+    // blockIdx.x enumerates (hrest: 8 bits, mbit: 1 bit (M in {2,3}), lrest: 8 bits) = 2^17 tiles
+    const uint32_t t = blockIdx.x;
+    const uint32_t lrest = t & 0xFFu, mlow = (t >> 8) & 1u, hrest = t >> 9;
+    const uint32_t M = 2u | mlow;                       // destination middle base has its high bit set
+    const uint32_t src_hrest = rc_small(lrest, 4);       // source H = (rc3(b) | rc4(lrest))
+    const uint32_t src_lrest = rc_small(hrest, 4);       // source L = (rc4(hrest) | rc3(a))
+    const uint32_t src_M = M ^ 2u;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+    // load: row = sb (source's top-3-bases value), col = sa (source's low-3-bases value)
+    for (int sb = ty; sb < 64; sb += 4) {
+        const uint32_t src = ((((uint32_t)sb << 8) | src_hrest) << 16) | (src_M << 14) | (src_lrest << 6) | (uint32_t)tx;
+        tile[sb][tx] = table[src];
+    }
+    __syncthreads();
+    // store: destination row a (top 3 bases of H), column b (low 3 bases of L); source coords are rc3 of them
+    for (int a = ty; a < 64; a += 4) {
+        const uint32_t dst = ((((uint32_t)a << 8) | hrest) << 16) | (M << 14) | (lrest << 6) | (uint32_t)tx;
+        table[dst] = tile[rc_small((uint32_t)tx, 3)][rc_small((uint32_t)a, 3)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// search: line_to_vec (kmer_utils.h:24-87)
+// ------------------------------------------------------------------------------------------------
+template <bool FILTER>
+__global__ void __launch_bounds__(kCtaThreads)
+k_search15(lrb_reads_view R, const uint32_t* __restrict__ table, uint32_t S32, uint64_t magic, uint32_t B,
+           uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sums_out, uint64_t tile_lo, uint64_t tile_hi,
+           uint32_t key_lo, uint32_t key_hi) {
+    extern __shared__ uint32_t s_dyn[];  // [kWarpsPerCta][B]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* hist = s_dyn + (size_t)warp * B;
+    for (uint32_t i = lane; i < B; i += 32) hist[i] = 0;
+    __syncwarp();
+
+    const uint64_t tile = tile_lo + (uint64_t)blockIdx.x * kWarpsPerCta + warp;
+    if (tile >= tile_hi) return;
+    const uint32_t r = R.tile_read[tile];
+    const uint32_t b0 = R.tile_blk[tile];
+    const uint32_t rb1 = R.read_blk[r + 1];
+    const uint32_t nblk = min((uint32_t)kTileBlocks, rb1 - b0);
+    const uint2* codes2 = reinterpret_cast<const uint2*>(R.codes);
+    uint32_t nwin = 0;
+
+    for (uint32_t i = lane; i < nblk; i += 32) {
+        const uint32_t gb = b0 + i;
+        const uint32_t v = ld_stream_u32(R.valid + gb);
+        const uint32_t pv = gb ? ld_stream_u32(R.valid + gb - 1) : 0u;
+        uint32_t m = window15_mask(pv, v);
+        if (m == 0) continue;
+        const uint2 w = ld_stream_u2(codes2 + gb);
+        const uint32_t pw = gb ? ld_stream_u32(R.codes + 2 * (size_t)gb - 1) : 0u;
+        uint32_t cnt[32];
+        if (FILTER) {
+            const uint32_t r0 = rc16(w.y), r1 = rc16(w.x), r2 = rc16(pw);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                cnt[j] = 0;
+                if ((m >> j) & 1u) {
+                    const uint32_t val = kmer_ending_at<15>(pw, w.x, w.y, j);
+                    const uint32_t key = canonical15(val, rc15_ending_at(r0, r1, r2, j));
+                    if (key >= key_lo && key < key_hi) cnt[j] = __ldg(table + key);
+                    else m &= ~(1u << j);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                cnt[j] = 0;
+                if ((m >> j) & 1u) cnt[j] = __ldg(table + kmer_ending_at<15>(pw, w.x, w.y, j));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if ((m >> j) & 1u) atomicAdd(&hist[coverage_bin(cnt[j], S32, magic, B)], 1u);
+        nwin += (uint32_t)popc32(m);
+    }
+    __syncwarp();
+    uint32_t* row = hist_out + (size_t)r * B;
+    for (uint32_t i = lane; i < B; i += 32) {
+        const uint32_t c = hist[i];
+        if (c) atomicAdd(row + i, c);
+    }
+    nwin = __reduce_add_sync(0xFFFFFFFFu, nwin);
+    if (lane == 0 && nwin) atomicAdd(sums_out + r, nwin);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ASCII -> packed on the device (same rule as the host packer in ingest.cpp)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_ascii(lrb_reads_view R, const char* __restrict__ bases, const uint64_t* __restrict__ offsets,
+             uint32_t* __restrict__ codes, uint32_t* __restrict__ valid) {
+    // one warp per read, lanes take blocks
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R.n_reads) return;
+    const uint32_t rb0 = R.read_blk[r], rb1 = R.read_blk[r + 1], len = R.read_len[r];
+    const char* s = bases + offsets[r];
+    for (uint32_t b = rb0 + lane; b < rb1; b += 32) {
+        const uint32_t p0 = (b - rb0) * 32u;
+        uint32_t w0 = 0, w1 = 0, v = 0;
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t p = p0 + j;
+            if (p < len) {
+                const unsigned char c = (unsigned char)s[p];
+                const uint32_t code = (c >> 1) & 3u;
+                if (j < 16) w0 |= code << (30 - 2 * j); else w1 |= code << (62 - 2 * j);
+                if (c == 'A' || c == 'C' || c == 'G' || c == 'T') v |= 1u << j;
+            }
+        }
+        codes[2 * (size_t)b] = w0;
+        codes[2 * (size_t)b + 1] = w1;
+        valid[b] = v;
+    }
+}
+
+thread_local bool t_luts_ready[64] = {false};
+
+int ensure_luts() {
+    int dev = 0;
+    LRB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && t_luts_ready[dev]) return LRB_OK;
+    uint16_t l3[64], l4[256], l5[1024];
+    lrb_kmer_lut(3, l3);
+    lrb_kmer_lut(4, l4);
+    lrb_kmer_lut(5, l5);
+    LRB_CUDA(cudaMemcpyToSymbol(g_lut3, l3, sizeof l3));
+    LRB_CUDA(cudaMemcpyToSymbol(g_lut4, l4, sizeof l4));
+    LRB_CUDA(cudaMemcpyToSymbol(g_lut5, l5, sizeof l5));
+    if (dev < 64) t_luts_ready[dev] = true;
+    return LRB_OK;
+}
+
+int sm_count() {
+    static thread_local int sms[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return 148;
+    if (!sms[dev]) {
+        if (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
+    }
+    return sms[dev];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI launchers
+// ------------------------------------------------------------------------------------------------
+extern "C" int lrb_dev_composition(const lrb_reads_view* dev, int k, uint32_t* counts, uint64_t tile_lo,
+                                   uint64_t tile_hi, void* stream) {
+    if (!dev || !counts || k < 3 || k > 5) return lrb_set_error(LRB_EINVAL, "lrb_dev_composition: k must be 3, 4 or 5");
+    if (tile_hi > dev->n_tiles) tile_hi = dev->n_tiles;
+    if (tile_lo >= tile_hi) return LRB_OK;
+    int rc = ensure_luts();
+    if (rc) return rc;
+    const uint64_t ntile = tile_hi - tile_lo;
+    const unsigned grid = (unsigned)((ntile + kWarpsPerCta - 1) / kWarpsPerCta);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k == 3) k_composition<3><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi);
+    else if (k == 4) k_composition<4><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi);
+    else k_composition<5><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_t blk_lo, uint64_t blk_hi,
+                             uint32_t key_lo, uint32_t key_hi, void* stream) {
+    if (!dev || !table) return lrb_set_error(LRB_EINVAL, "lrb_dev_count: null argument");
+    if (blk_hi > dev->n_blocks) blk_hi = dev->n_blocks;
+    if (blk_lo >= blk_hi || key_lo >= key_hi) return LRB_OK;
+    const uint64_t nblk = blk_hi - blk_lo;
+    const int threads = 256;
+    uint64_t want = (nblk + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sm_count() * 16;  // persistent grid: 16 CTAs of 256 threads per SM
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool filter = !(key_lo == 0 && key_hi >= kTableEntries);
+    if (filter) k_count15<true><<<grid, threads, 0, st>>>(dev->codes, dev->valid, table, blk_lo, blk_hi, key_lo, key_hi);
+    else k_count15<false><<<grid, threads, 0, st>>>(dev->codes, dev->valid, table, blk_lo, blk_hi, key_lo, key_hi);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_mirror(uint32_t* table, void* stream) {
+    if (!table) return lrb_set_error(LRB_EINVAL, "lrb_dev_mirror: null table");
+    k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_size, int bins,
+                              uint32_t* hist, uint32_t* sums, uint64_t tile_lo, uint64_t tile_hi, uint32_t key_lo,
+                              uint32_t key_hi, void* stream) {
+    if (!dev || !table || !hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_search: null argument");
+    if (bin_size <= 0) return lrb_set_error(LRB_EINVAL, "lrb_dev_search: bin_size must be >= 1 (the reference divides by it)");
+    if (bins <= 0 || bins > LRB_MAX_BINS) return lrb_set_error(LRB_EINVAL, "lrb_dev_search: bins must be in [1, 4096]");
+    if (tile_hi > dev->n_tiles) tile_hi = dev->n_tiles;
+    if (tile_lo >= tile_hi || key_lo >= key_hi) return LRB_OK;
+    const uint32_t S32 = bin_size > 0xFFFFFFFFl ? 0xFFFFFFFFu : (uint32_t)bin_size;
+    const uint64_t magic = coverage_magic(S32);
+    const uint64_t ntile = tile_hi - tile_lo;
+    const unsigned grid = (unsigned)((ntile + kWarpsPerCta - 1) / kWarpsPerCta);
+    const size_t smem = (size_t)kWarpsPerCta * (size_t)bins * sizeof(uint32_t);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool filter = !(key_lo == 0 && key_hi >= kTableEntries);
+    if (smem > 48 * 1024) {
+        LRB_CUDA(cudaFuncSetAttribute(k_search15<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LRB_CUDA(cudaFuncSetAttribute(k_search15<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (filter)
+        k_search15<true><<<grid, kCtaThreads, smem, st>>>(*dev, table, S32, magic, (uint32_t)bins, hist, sums, tile_lo, tile_hi, key_lo, key_hi);
+    else
+        k_search15<false><<<grid, kCtaThreads, smem, st>>>(*dev, table, S32, magic, (uint32_t)bins, hist, sums, tile_lo, tile_hi, key_lo, key_hi);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, const uint64_t* offsets, void* stream) {
+    if (!dev || !bases || !offsets) return lrb_set_error(LRB_EINVAL, "lrb_dev_pack_ascii: null argument");
+    if (dev->n_reads == 0) return LRB_OK;
+    const uint64_t threads = dev->n_reads * 32;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    k_pack_ascii<<<grid, 256, 0, (cudaStream_t)stream>>>(*dev, bases, offsets, const_cast<uint32_t*>(dev->codes),
+                                                        const_cast<uint32_t*>(dev->valid));
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
