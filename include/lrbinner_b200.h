@@ -84,7 +84,7 @@ void lrb_reads_free(lrb_reads* r);
 
 /* count_kmers (count-kmers.cpp:66-95): counts[N*P] += raw canonical k-mer counts, P = 32/136/512 for
  * k = 3/4/5.  counts must be zeroed by the caller (the call accumulates). EVERY byte of a read takes part
- * (no ACGT check), total windows per read = max(0, len-k+1). Restricted to reads [read_lo, read_hi). */
+ * (no ACGT check), total windows per read = max(0, len-k+1). Restricted to tiles [tile_lo, tile_hi). */
 int lrb_dev_composition(const lrb_reads_view* dev, int k, uint32_t* counts, uint64_t tile_lo, uint64_t tile_hi,
                         void* stream);
 
@@ -98,8 +98,10 @@ int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_t blk_lo, u
 int lrb_dev_mirror(uint32_t* table, void* stream);
 
 /* line_to_vec (kmer_utils.h:24-87): hist[N*bins] += bucket counts, sums[N] += valid windows, for the
- * reads of tiles [tile_lo, tile_hi).  Looks up table[val] (forward key) — table must be mirrored —
- * restricted to windows whose canonical key lies in [key_lo, key_hi) (pass 0, 2^30 for all).
+ * reads of tiles [tile_lo, tile_hi).  With key range [0, 2^30) every valid window looks up table[val]
+ * (forward key; the table must be mirrored).  With a narrower range (key-sharded search) only windows
+ * whose bit-15-clear key c lies in [key_lo, key_hi) are bucketed, through table[c] (no mirror needed);
+ * summing hist/sums over a partition of the key space gives the full result.
  * hist/sums must be zeroed by the caller. */
 int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_size, int bins, uint32_t* hist,
                    uint32_t* sums, uint64_t tile_lo, uint64_t tile_hi, uint32_t key_lo, uint32_t key_hi, void* stream);
@@ -123,6 +125,7 @@ typedef struct {
     uint64_t seed;
     uint32_t n_genomes;
     uint32_t sub_thr, ins_thr, del_thr, n_thr;
+    uint64_t read_base;   /* global index of read 0 (lets shards of one community be generated apart) */
 } lrb_synth_params;
 int lrb_dev_synth(const lrb_reads_view* dev, const lrb_synth_params* p, const uint32_t* glen, const uint32_t* meta,
                   void* stream);
@@ -147,6 +150,9 @@ int lrb_profile_host(lrb_ctx* ctx, const lrb_reads* reads, int k, long bin_size,
 /* Per-phase device milliseconds of the last lrb_profile_host call:
  * [0] h2d [1] composition [2] memset+count [3] mirror [4] search [5] d2h [6] total */
 int lrb_ctx_last_timings(const lrb_ctx* ctx, float* ms7);
+/* page-locked host memory for result buffers of lrb_profile_host (NULL + lrb_last_error on failure) */
+void* lrb_pinned_alloc(size_t bytes);
+void lrb_pinned_free(void* p);
 int lrb_ctx_table_load(lrb_ctx* ctx, const char* path);          /* readKmerFile -> HBM */
 int lrb_ctx_table_save(lrb_ctx* ctx, const char* path);          /* HBM -> writeKmerFile format */
 

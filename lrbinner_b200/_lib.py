@@ -1,0 +1,100 @@
+"""ctypes binding of liblrb200.so (C ABI in include/lrbinner_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import, and any
+compute entry point returns LRB_ECUDA when no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblrb200.so")
+
+LRB_OK, LRB_EINVAL, LRB_EIO, LRB_ECUDA, LRB_ENOMEM, LRB_EFORMAT = range(6)
+TABLE_ENTRIES = 1 << 30
+TILE_BLOCKS = 256
+MAX_BINS = 4096
+
+
+class LrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblrb200 error {code}: {msg}")
+        self.code = code
+
+
+class ReadsView(C.Structure):
+    """lrb_reads_view: sizes + raw pointers (host or device, depending on who filled it)."""
+    _fields_ = [("n_reads", C.c_uint64), ("n_blocks", C.c_uint64), ("n_tiles", C.c_uint64), ("total_bases", C.c_uint64),
+                ("codes", C.c_void_p), ("valid", C.c_void_p), ("read_len", C.c_void_p), ("read_blk", C.c_void_p),
+                ("tile_read", C.c_void_p), ("tile_blk", C.c_void_p)]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_genomes", C.c_uint32), ("sub_thr", C.c_uint32), ("ins_thr", C.c_uint32),
+                ("del_thr", C.c_uint32), ("n_thr", C.c_uint32), ("read_base", C.c_uint64)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+        "`make -C lrbinner_b200/csrc` (nvcc, sm_100a). lrbinner_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_P = C.c_void_p
+_SIG = {
+    "lrb_version": (C.c_int, []),
+    "lrb_last_error": (C.c_char_p, []),
+    "lrb_reads_from_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "lrb_reads_from_ascii": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.POINTER(_P)]),
+    "lrb_reads_from_lengths": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
+    "lrb_reads_view_get": (C.c_int, [_P, C.POINTER(ReadsView)]),
+    "lrb_reads_unpack": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "lrb_reads_free": (None, [_P]),
+    "lrb_dev_composition": (C.c_int, [C.POINTER(ReadsView), C.c_int, _P, C.c_uint64, C.c_uint64, _P]),
+    "lrb_dev_count": (C.c_int, [C.POINTER(ReadsView), _P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P]),
+    "lrb_dev_mirror": (C.c_int, [_P, _P]),
+    "lrb_dev_search": (C.c_int, [C.POINTER(ReadsView), _P, C.c_long, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
+                                 C.c_uint32, C.c_uint32, _P]),
+    "lrb_dev_pack_ascii": (C.c_int, [C.POINTER(ReadsView), _P, _P, _P]),
+    "lrb_dev_format_composition": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
+    "lrb_dev_format_coverage": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
+    "lrb_dev_synth": (C.c_int, [C.POINTER(ReadsView), C.POINTER(SynthParams), _P, _P, _P]),
+    "lrb_synth_host": (C.c_int, [C.POINTER(SynthParams), _P, _P, _P, C.c_uint64, _P, _P]),
+    "lrb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "lrb_ctx_destroy": (None, [_P]),
+    "lrb_profile_host": (C.c_int, [_P, _P, C.c_int, C.c_long, C.c_int, _P, _P, _P, _P, C.c_int]),
+    "lrb_ctx_last_timings": (C.c_int, [_P, _P]),
+    "lrb_pinned_alloc": (_P, [C.c_size_t]),
+    "lrb_pinned_free": (None, [_P]),
+    "lrb_ctx_table_load": (C.c_int, [_P, C.c_char_p]),
+    "lrb_ctx_table_save": (C.c_int, [_P, C.c_char_p]),
+    "lrb_fixed6": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_int]),
+    "lrb_write_composition_txt": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.c_int, C.c_int]),
+    "lrb_write_coverage_txt": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.c_int, C.c_int]),
+    "lrb_write_composition_npy": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.c_int, C.c_int]),
+    "lrb_write_coverage_npy": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.c_int, C.c_int]),
+    "lrb_table_write_file": (C.c_int, [C.c_char_p, _P]),
+    "lrb_table_read_file": (C.c_int, [C.c_char_p, _P]),
+    "lrb_kmer_lut": (C.c_int, [C.c_int, _P]),
+    "lrb_count_kmers": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
+    "lrb_count_15mers": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
+    "lrb_search_15mers": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_long, C.c_int, C.c_int]),
+    "lrb_profile": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int]),
+}
+
+EXPORTS = tuple(_SIG)
+
+for _name, (_res, _args) in _SIG.items():
+    _fn = getattr(lib, _name)   # AttributeError here == the .so does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error():
+    return (lib.lrb_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc != 0:
+        raise LrbError(rc, last_error())
+    return rc

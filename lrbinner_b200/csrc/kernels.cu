@@ -16,6 +16,7 @@
 #include "../../include/lrbinner_b200.h"
 #include "common.h"
 #include "lane_core.cuh"
+#include "fixed6.h"
 
 using namespace lrb;
 
@@ -69,17 +70,8 @@ k_composition(lrb_reads_view R, uint32_t* __restrict__ out, uint64_t tile_lo, ui
         const uint2 w = ld_stream_u2(codes2 + gb);
         const uint32_t p0 = (gb - rb0) * 32u;            // read position of slot 0 of this block
         const uint32_t pw = (p0 != 0) ? ld_stream_u32(R.codes + 2 * (size_t)gb - 1) : 0u;
-        const uint32_t n_in = min(32u, len - p0);        // in-read slots of this block (0..32)
-        uint32_t m = (n_in >= 32u) ? 0xFFFFFFFFu : ((1u << n_in) - 1u);
-        if (p0 == 0) m &= ~((1u << (K - 1)) - 1u);       // first K-1 positions of a read end no window
-        if (m == 0xFFFFFFFFu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(&hist[s_lut[kmer_ending_at<K>(pw, w.x, w.y, j)]], 1u);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if ((m >> j) & 1u) atomicAdd(&hist[s_lut[kmer_ending_at<K>(pw, w.x, w.y, j)]], 1u);
-        }
+        const uint32_t m = comp_block_mask(p0, len, K);
+        comp_block<K>(pw, w.x, w.y, m, [&](uint32_t kmer) { atomicAdd(&hist[s_lut[kmer]], 1u); });
     }
     __syncwarp();
     uint32_t* row = out + (size_t)r * P;
@@ -105,46 +97,22 @@ k_count15(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid
         if (m == 0) continue;
         const uint2 w = ld_stream_u2(codes2 + gb);
         const uint32_t pw = gb ? ld_stream_u32(codes + 2 * gb - 1) : 0u;
-        const uint32_t r0 = rc16(w.y), r1 = rc16(w.x), r2 = rc16(pw);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if ((m >> j) & 1u) {
-                const uint32_t val = kmer_ending_at<15>(pw, w.x, w.y, j);
-                const uint32_t key = canonical15(val, rc15_ending_at(r0, r1, r2, j));
-                if (!FILTER || (key >= key_lo && key < key_hi)) atomicAdd(table + key, 1u);
-            }
-        }
+        canon15_block(pw, w.x, w.y, m, [&](uint32_t key) {
+            if (!FILTER || (key >= key_lo && key < key_hi)) atomicAdd(table + key, 1u);
+        });
     }
 }
 
-// mirror: T[x] = T[rc(x)] for all x with bit 15 set.  x = (H:14 | M:2 | L:14) -> rc(x) = (rc7(L) | M^2 | rc7(H)).
-// CTA tile: H = (a | hrest), L = (lrest | b) with a = top 3 bases of H, b = low 3 bases of L (64 values each).
-// Source rows are indexed by rc3(b) (high bases of the source H) and hold 64 contiguous entries indexed by rc3(a).
-__device__ __forceinline__ uint32_t rc_small(uint32_t x, int nbases) {  // reverse-complement of nbases (<=16) bases
-    return rc16(x << (32 - 2 * nbases)) & ((1u << (2 * nbases)) - 1u);
-}
-
+// mirror: T[x] = T[rc(x)] for all x with bit 15 set — a 64x64 tiled "transpose" whose index algebra
+// (mirror_dst_index / mirror_src_index) lives in lane_core.cuh.  Reads touch only bit-15-clear entries,
+// writes only bit-15-set ones, so the pass is race-free in place; both sides move 256 B rows.
 __global__ void __launch_bounds__(256) k_mirror(uint32_t* __restrict__ table) {
     __shared__ uint32_t tile[64][65];
-    // blockIdx.x enumerates (hrest: 8 bits, mbit: 1 bit (M in {2,3}), lrest: 8 bits) = 2^17 tiles
     const uint32_t t = blockIdx.x;
-    const uint32_t lrest = t & 0xFFu, mlow = (t >> 8) & 1u, hrest = t >> 9;
-    const uint32_t M = 2u | mlow;                       // destination middle base has its high bit set
-    const uint32_t src_hrest = rc_small(lrest, 4);       // source H = (rc3(b) | rc4(lrest))
-    const uint32_t src_lrest = rc_small(hrest, 4);       // source L = (rc4(hrest) | rc3(a))
-    const uint32_t src_M = M ^ 2u;
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
-    // load: row = sb (source's top-3-bases value), col = sa (source's low-3-bases value)
-    for (int sb = ty; sb < 64; sb += 4) {
-        const uint32_t src = ((((uint32_t)sb << 8) | src_hrest) << 16) | (src_M << 14) | (src_lrest << 6) | (uint32_t)tx;
-        tile[sb][tx] = table[src];
-    }
+    const uint32_t tx = threadIdx.x & 63u, ty = threadIdx.x >> 6;  // 64 x 4
+    for (uint32_t sb = ty; sb < 64; sb += 4) tile[sb][tx] = table[mirror_src_index(t, sb, tx)];
     __syncthreads();
-    // store: destination row a (top 3 bases of H), column b (low 3 bases of L); source coords are rc3 of them
-    for (int a = ty; a < 64; a += 4) {
-        const uint32_t dst = ((((uint32_t)a << 8) | hrest) << 16) | (M << 14) | (lrest << 6) | (uint32_t)tx;
-        table[dst] = tile[rc_small((uint32_t)tx, 3)][rc_small((uint32_t)a, 3)];
-    }
+    for (uint32_t a = ty; a < 64; a += 4) table[mirror_dst_index(t, a, tx)] = tile[rc_small(tx, 3)][rc_small(a, 3)];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,6 +209,36 @@ k_pack_ascii(lrb_reads_view R, const char* __restrict__ bases, const uint64_t* _
         codes[2 * (size_t)b + 1] = w1;
         valid[b] = v;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// text epilogue: fixed-width "%f" rows (count-kmers.cpp:110-118, search-15mers.cpp:35-48)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_fixed6_dev(char* dst, uint32_t q, char sep) {  // "d.dddddd" + sep
+    dst[0] = (char)('0' + q / 1000000u);
+    dst[1] = '.';
+    uint32_t f = q % 1000000u;
+#pragma unroll
+    for (int i = 7; i >= 2; --i) { dst[i] = (char)('0' + f % 10u); f /= 10u; }
+    dst[8] = sep;
+}
+
+// one thread per value; COMP: value followed by ' ' and a '\n' closes the row; coverage: ' ' between, '\n' last
+template <bool COMP>
+__global__ void __launch_bounds__(256)
+k_format_rows(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ denom_src, uint64_t n_rows, uint32_t width,
+              int k, char* __restrict__ text) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * width) return;
+    const uint64_t r = idx / width;
+    const uint32_t j = (uint32_t)(idx - r * width);
+    uint32_t den = denom_src[r];
+    if (COMP) den = den >= (uint32_t)k ? den - (uint32_t)k + 1u : 0u;  // total = max(0, len-k+1)
+    const uint32_t q = fixed6(counts[idx], den, !COMP);
+    const size_t row_bytes = COMP ? (size_t)width * 9 + 1 : (size_t)width * 9;
+    char* dst = text + r * row_bytes + (size_t)j * 9;
+    put_fixed6_dev(dst, q, (!COMP && j == width - 1) ? '\n' : ' ');
+    if (COMP && j == width - 1) dst[9] = '\n';
 }
 
 thread_local bool t_luts_ready[64] = {false};
@@ -351,6 +349,27 @@ extern "C" int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, 
     const unsigned grid = (unsigned)((threads + 255) / 256);
     k_pack_ascii<<<grid, 256, 0, (cudaStream_t)stream>>>(*dev, bases, offsets, const_cast<uint32_t*>(dev->codes),
                                                         const_cast<uint32_t*>(dev->valid));
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_format_composition(const uint32_t* counts, const uint32_t* read_len, uint64_t n_reads, int k,
+                                          char* text, void* stream) {
+    const int P = (k == 3) ? 32 : (k == 4) ? 136 : (k == 5) ? 512 : 0;
+    if (!P || !text || (n_reads && (!counts || !read_len))) return lrb_set_error(LRB_EINVAL, "lrb_dev_format_composition: bad argument");
+    if (!n_reads) return LRB_OK;
+    const uint64_t total = n_reads * (uint64_t)P;
+    k_format_rows<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, read_len, n_reads, (uint32_t)P, k, text);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_format_coverage(const uint32_t* hist, const uint32_t* sums, uint64_t n_reads, int bins, char* text,
+                                       void* stream) {
+    if (bins <= 0 || !text || (n_reads && (!hist || !sums))) return lrb_set_error(LRB_EINVAL, "lrb_dev_format_coverage: bad argument");
+    if (!n_reads) return LRB_OK;
+    const uint64_t total = n_reads * (uint64_t)bins;
+    k_format_rows<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hist, sums, n_reads, (uint32_t)bins, 0, text);
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

@@ -131,4 +131,51 @@ LRB_HD uint32_t coverage_bin(uint32_t count, uint32_t S32, uint64_t magic, uint3
 
 inline uint64_t coverage_magic(uint32_t S32) { return S32 <= 1u ? 0ull : (~0ull / S32) + 1ull; }
 
+// ---- per-block drivers (one lane, one 32-slot block) -------------------------------------------
+
+// composition (count-kmers.cpp:73-87): which slots of the block END a k-mer window.  p0 = read position
+// of slot 0 (a multiple of 32), len = read length.  No validity test: every byte takes part.
+LRB_HD uint32_t comp_block_mask(uint32_t p0, uint32_t len, int k) {
+    const uint32_t n_in = (len - p0) < 32u ? (len - p0) : 32u;  // in-read slots of this block (p0 <= len)
+    uint32_t m = (n_in >= 32u) ? 0xFFFFFFFFu : ((1u << n_in) - 1u);
+    if (p0 == 0) m &= ~((1u << (k - 1)) - 1u);  // the first k-1 positions of a read end no window
+    return m;
+}
+
+template <int K, class F>
+LRB_HD void comp_block(uint32_t pw, uint32_t w0, uint32_t w1, uint32_t m, F f) {
+    if (m == 0xFFFFFFFFu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f(kmer_ending_at<K>(pw, w0, w1, j));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if ((m >> j) & 1u) f(kmer_ending_at<K>(pw, w0, w1, j));
+    }
+}
+
+// 15-mer windows of a block: f(key) with key = the bit-15-clear member of {val, rc(val)}
+template <class F>
+LRB_HD void canon15_block(uint32_t pw, uint32_t w0, uint32_t w1, uint32_t m, F f) {
+    const uint32_t r0 = rc16(w1), r1 = rc16(w0), r2 = rc16(pw);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+        if ((m >> j) & 1u) f(canonical15(kmer_ending_at<15>(pw, w0, w1, j), rc15_ending_at(r0, r1, r2, j)));
+}
+
+// mirror pass index algebra.  Table index x = (H:14 | M:2 | L:14); rc(x) = (rc7(L) | M^2 | rc7(H)).
+// Tile t in [0, 2^17) = (hrest:8 | mlow:1 | lrest:8); destination H = (a:6 | hrest), L = (lrest | b:6),
+// M = 2|mlow (bit 15 set).  The source tile holds rows sb = rc3(b) of 64 contiguous entries sa = rc3(a).
+LRB_HD uint32_t rc_small(uint32_t x, int nbases) {  // reverse complement of nbases (<= 16) bases
+    return rc16(x << (32 - 2 * nbases)) & ((1u << (2 * nbases)) - 1u);
+}
+LRB_HD uint32_t mirror_dst_index(uint32_t t, uint32_t a, uint32_t b) {
+    const uint32_t lrest = t & 0xFFu, mlow = (t >> 8) & 1u, hrest = t >> 9;
+    return (((a << 8) | hrest) << 16) | ((2u | mlow) << 14) | (lrest << 6) | b;
+}
+LRB_HD uint32_t mirror_src_index(uint32_t t, uint32_t sb, uint32_t sa) {
+    const uint32_t lrest = t & 0xFFu, mlow = (t >> 8) & 1u, hrest = t >> 9;
+    return (((sb << 8) | rc_small(lrest, 4)) << 16) | (mlow << 14) | (rc_small(hrest, 4) << 6) | sa;
+}
+
 }  // namespace lrb

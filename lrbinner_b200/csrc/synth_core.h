@@ -38,7 +38,7 @@ LRB_HD void synth_read(const lrb_synth_params& p, const uint32_t* glen, uint64_t
     const bool rev = flags & 1u, lower = flags & 2u;
     uint32_t gpos = start % gl;
     uint64_t ctr = 0;
-    const uint64_t rkey = mix64(p.seed ^ 0xA5A5A5A5ull) ^ (r * 0x9E3779B97F4A7C15ull);
+    const uint64_t rkey = mix64(p.seed ^ 0xA5A5A5A5ull) ^ ((r + p.read_base) * 0x9E3779B97F4A7C15ull);
     const uint32_t t_del = p.del_thr, t_ins = t_del + p.ins_thr, t_sub = t_ins + p.sub_thr;
     for (uint32_t out = 0; out < len;) {
         const uint64_t h = mix64(rkey + ctr++);

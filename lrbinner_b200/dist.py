@@ -1,0 +1,270 @@
+"""Multi-GPU profile stage: one process per GPU, torch.distributed (NCCL over NVLink) for the exchanges.
+
+Reads are independent for composition; the 15-mer table is a commutative u32 sum; the search is a gather
+against the finished table.  Three decompositions are implemented and timed
+(bench.py keeps the fastest on measured numbers, as BASELINE.json's north star asks):
+
+  plan "keyshard_rs" (A)  key space split by the high bits of the 30-bit key: rank g owns
+        T[g*2^30/G, (g+1)*2^30/G).  COUNT: every rank scans all reads and increments only its own keys —
+        no communication.  SEARCH: every rank buckets only the windows whose key it owns into partial
+        u32[N,B] histograms (+ partial sums[N]); reduce-scatter(sum) leaves each rank the final rows of its
+        own N/G reads.
+  plan "keyshard_ag" (B)  COUNT as in A, then all-gather of the table slices (4 GiB in total), local
+        mirror, read-sharded SEARCH with no further communication.
+  plan "readshard_ar" (X) every rank counts only ITS reads into a private full table; all-reduce(sum) of the
+        4 GiB tables; local mirror; read-sharded SEARCH.  No rank needs another rank's reads.
+
+u32 sums are associative mod 2^32, so every plan is bit-exact whatever the reduction order.
+Composition is read-sharded in all plans.  Each rank returns the rows of its own reads
+[own_lo, own_hi) = equal contiguous chunks of ceil(N/G) reads.
+
+The engine argument does the per-GPU work.  The product engine is CudaEngine (lrb_dev_* kernels); the
+CPU tests inject an oracle-backed engine to check the sharding / collective logic over gloo.
+"""
+import numpy as np
+
+TABLE_ENTRIES = 1 << 30
+PLANS = ("keyshard_rs", "keyshard_ag", "readshard_ar")
+
+
+def chunk_size(n, world):
+    return (n + world - 1) // world
+
+
+def own_range(n, world, rank):
+    c = chunk_size(n, world)
+    return min(n, rank * c), min(n, (rank + 1) * c)
+
+
+def key_range(world, rank, entries=TABLE_ENTRIES):
+    return rank * entries // world, (rank + 1) * entries // world
+
+
+class CudaEngine:
+    """Per-GPU work through the C ABI kernels on torch CUDA tensors (the product path)."""
+
+    def __init__(self, device_reads):
+        import torch
+        from . import profile
+        self.torch, self.p, self.dr = torch, profile, device_reads
+        self.n_reads = device_reads.n_reads
+        self.device = device_reads.device
+        self.table_entries = TABLE_ENTRIES          # 4^15 (count-15mers.cpp:99)
+        self._rb = None
+
+    def zeros(self, shape):
+        return self.torch.zeros(shape, dtype=self.torch.int32, device=self.device)
+
+    def _blocks(self, lo, hi):
+        if self._rb is None:
+            self._rb = self.dr.read_blk.cpu().numpy().view(np.uint32)
+        return int(self._rb[lo]), int(self._rb[hi])
+
+    def composition(self, k, comp, read_lo, read_hi):
+        tlo, thi = self.dr.tile_range_for_reads(read_lo, read_hi)
+        self.p.dev_composition(self.dr, k, comp, tlo, thi)
+
+    def count(self, table, key_lo, key_hi, read_lo, read_hi):
+        blo, bhi = self._blocks(read_lo, read_hi)
+        self.p.dev_count(self.dr, table, blo, bhi, key_lo, key_hi)
+
+    def mirror(self, table):
+        self.p.dev_mirror(table)
+
+    def search(self, table, bin_size, bins, hist, sums, read_lo, read_hi, key_lo, key_hi):
+        tlo, thi = self.dr.tile_range_for_reads(read_lo, read_hi)
+        self.p.dev_search(self.dr, table, bin_size, bins, hist, sums, tlo, thi, key_lo, key_hi)
+
+
+def _reduce_scatter(dist, out, inp, group):
+    """out = this rank's chunk of sum over ranks of inp (gloo has no reduce_scatter: all_reduce + slice)."""
+    if dist.get_backend(group) == "gloo":
+        dist.all_reduce(inp, group=group)
+        r = dist.get_rank(group)
+        out.copy_(inp[r * out.shape[0]:(r + 1) * out.shape[0]])
+    else:
+        dist.reduce_scatter_tensor(out, inp, group=group)
+
+
+def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None, comp_width=None, timers=None):
+    """Runs the whole stage across the ranks of `group`.  Returns dict(comp, hist, sums, own=(lo, hi), table):
+    comp/hist/sums hold the rows of this rank's own reads (row i <-> read own_lo + i)."""
+    import torch.distributed as dist
+    assert plan in PLANS, plan
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = engine.n_reads
+    c = chunk_size(n, world)
+    lo, hi = own_range(n, world, rank)
+    entries = engine.table_entries
+    klo, khi = key_range(world, rank, entries)
+    P = comp_width if comp_width is not None else {3: 32, 4: 136, 5: 512}[k]
+    mark = timers.mark if timers else (lambda name: None)
+
+    # composition: read-sharded, no exchange.  Rows are written at their global index; return the own slice.
+    comp_all = engine.zeros((n, P))
+    if hi > lo:
+        engine.composition(k, comp_all, lo, hi)
+    comp = comp_all[lo:hi]
+    mark("composition")
+
+    if table is None:
+        table = engine.zeros((entries,))
+    else:
+        table.zero_()
+    if plan == "readshard_ar":
+        if hi > lo:
+            engine.count(table, 0, entries, lo, hi)
+        mark("count")
+        dist.all_reduce(table, group=group)                      # 4 GiB u32 sum over NVLink
+        mark("exchange_table")
+    else:
+        engine.count(table, klo, khi, 0, n)                       # all reads, own keys: no communication
+        mark("count")
+        if plan == "keyshard_ag":
+            dist.all_gather_into_tensor(table, table[klo:khi].clone(), group=group)   # 2^30/G entries per rank -> 4 GiB everywhere
+            mark("exchange_table")
+
+    if plan == "keyshard_rs":
+        part_h = engine.zeros((world * c, bins))
+        part_s = engine.zeros((world * c,))
+        engine.search(table, bin_size, bins, part_h, part_s, 0, n, klo, khi)   # partial histograms over own keys
+        mark("search")
+        hist = engine.zeros((c, bins))
+        sums = engine.zeros((c,))
+        _reduce_scatter(dist, hist, part_h, group)
+        _reduce_scatter(dist, sums, part_s, group)
+        hist, sums = hist[:hi - lo], sums[:hi - lo]
+        mark("exchange_hist")
+    else:
+        engine.mirror(table)
+        mark("mirror")
+        hist_all = engine.zeros((n, bins))
+        sums_all = engine.zeros((n,))
+        if hi > lo:
+            engine.search(table, bin_size, bins, hist_all, sums_all, lo, hi, 0, entries)
+        hist, sums = hist_all[lo:hi], sums_all[lo:hi]
+        mark("search")
+    return {"comp": comp, "hist": hist, "sums": sums, "own": (lo, hi), "table": table}
+
+
+class _EventTimers:
+    """CUDA-event phase timers on the current stream (the collectives are ordered against it by torch)."""
+
+    def __init__(self, torch):
+        self.torch, self.ev = torch, []
+        self.mark("start")
+
+    def mark(self, name):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ev.append((name, e))
+
+    def phases_ms(self):
+        out = {}
+        for (_, a), (name, b) in zip(self.ev[:-1], self.ev[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+
+def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_peak, peak_src, metric, bs, bc):
+    """N > 1 leg of bench.py: weak scaling — the global read set is `world` shards of the config's size drawn
+    from ONE community (one global 15-mer table).  Times every plan once, keeps the fastest for the K steps."""
+    import torch
+    import torch.distributed as dist
+    from .profile import COMP_WIDTH, DeviceReads
+    from .synth import SynthSpec
+
+    k = cfg["k"]
+    n_shard = args.reads or cfg["n_reads"]
+    # every rank materialises the whole global set in HBM (plans A/B scan all reads; plan X touches only its own)
+    spec = SynthSpec(n_shard * world, lengths=cfg["lengths"], errors=cfg["errors"], seed=cfg["seed"])
+    dr, layout = spec.device_reads(dev)
+    n, L = spec.n_reads, spec.total_bases
+    eng = CudaEngine(dr)
+    table = torch.zeros(TABLE_ENTRIES, dtype=torch.int32, device=dev)
+
+    def timed(plan, steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tm = None
+        for _ in range(steps):
+            tm = _EventTimers(torch)
+            res = profile_distributed(eng, k, bs, bc, plan, table=table, timers=tm)
+        b.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res, tm.phases_ms()
+
+    plan_ms, checks = {}, {}
+    for plan in PLANS:
+        timed(plan, 1)                                   # warm-up (NCCL channels, allocator)
+        plan_ms[plan], res, _ = timed(plan, max(1, args.warmup - 1))
+        tot = torch.stack([res["sums"].to(torch.int64).sum(), res["hist"].to(torch.int64).sum(), res["comp"].to(torch.int64).sum()])
+        dist.all_reduce(tot)
+        checks[plan] = [int(x) for x in tot.tolist()]
+    assert len({tuple(v) for v in checks.values()}) == 1, f"plans disagree: {checks}"
+    valid_windows = checks[PLANS[0]][0]
+    assert checks[PLANS[0]][1] == valid_windows
+    best = min(plan_ms, key=plan_ms.get)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms_step, res, phases = timed(best, args.steps)
+    clocks = sampler.stop()
+    launches = {"keyshard_rs": 3, "keyshard_ag": 4, "readshard_ar": 4}[best] * args.steps
+
+    # e2e: every step also moves this rank's inputs host->device and its result rows device->host
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    dr.download_into(layout)
+    h_codes, h_valid = torch.from_numpy(layout.codes.view(np.int32)), torch.from_numpy(layout.valid.view(np.int32))
+    if best == "readshard_ar":   # only the own shard's blocks are needed on this rank
+        lo, hi = own_range(n, world, rank)
+        rb = layout.read_blk
+        b0, b1 = int(rb[lo]), int(rb[hi])
+    else:
+        b0, b1 = 0, layout.n_blocks
+    out_h = {kk: pin(res[kk]) for kk in ("comp", "hist", "sums")}
+
+    def e2e_step():
+        dr.codes[2 * b0:2 * b1].copy_(h_codes[2 * b0:2 * b1], non_blocking=True)
+        dr.valid[b0:b1].copy_(h_valid[b0:b1], non_blocking=True)
+        r = profile_distributed(eng, k, bs, bc, best, table=table)
+        for kk in out_h:
+            out_h[kk].copy_(r[kk], non_blocking=True)
+
+    e2e_step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        e2e_step()
+    b.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    h2d = 4 * (2 * (b1 - b0)) + 4 * (b1 - b0)
+    d2h = sum(int(t.numel()) * 4 for t in out_h.values())
+
+    count_ms = phases.get("count", 0.0)
+    own_updates = valid_windows / world
+    alg = 0.375 * L * (1.0 if best != "readshard_ar" else 1.0 / world) + 16 * own_updates
+    line = {"metric": metric, "value": L / ms_step / 1e6, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{world} x {cfg_name} shards of one community (one global 15-mer table)", "reads": n, "bases": L,
+                       "k": k, "bin_size": bs, "bins": bc, "plan": best, "plan_ms": plan_ms, "valid_15mer_windows": valid_windows,
+                       "l2_policy": "inputs larger than L2"},
+            "e2e": {"value": L / e2e_ms / 1e6, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms, "note": "per-rank bytes; max-over-ranks time"},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "k_count15 (rank 0)", "bound": "hbm", "achieved": alg / max(count_ms, 1e-6) / 1e6 / 1.0 if count_ms else None,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": (alg / max(count_ms, 1e-6) / 1e6) / hbm_peak if count_ms else None,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": count_ms, "includes": "4 GiB table memset"},
+            "phases_ms_rank0": phases, "clocks": clocks, "cpu_baseline": None}
+    return line

@@ -1,0 +1,260 @@
+"""Buffer-level Python view of the profile stage (thin wrappers over the C ABI).
+
+  PackedReads  — a read set in the packed host layout (lrb_reads*), from a FASTA/FASTQ file, from
+                 ASCII bases, or layout-only from lengths.
+  Context      — one GPU: seam-to-seam `profile()` over host buffers (lrb_profile_host).
+  DeviceReads / dev_* — torch-tensor plumbing for the device-pointer level (lrb_dev_*): used by the
+                 device-resident benchmark and the multi-GPU driver (lrbinner_b200/dist.py), where
+                 torch.distributed needs tensors over the same memory.
+
+The arithmetic lives in the CUDA kernels; nothing here computes profiles on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ReadsView, check, lib
+
+COMP_WIDTH = {3: 32, 4: 136, 5: 512}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PackedReads:
+    """Owns an lrb_reads* (host memory, page-locked when a GPU is present)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.view = ReadsView()
+        check(lib.lrb_reads_view_get(self._h, C.byref(self.view)))
+
+    # -- constructors ---------------------------------------------------------------------------
+    @classmethod
+    def from_file(cls, path, threads=8):
+        h = C.c_void_p()
+        check(lib.lrb_reads_from_file(str(path).encode(), int(threads), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_sequences(cls, seqs, threads=8):
+        """seqs: iterable of bytes/str (one per read)."""
+        bs = [s if isinstance(s, (bytes, bytearray)) else s.encode("latin-1") for s in seqs]
+        offsets = np.zeros(len(bs) + 1, dtype=np.uint64)
+        if bs:
+            offsets[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+        bases = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8)
+        return cls.from_ascii(bases, offsets, threads)
+
+    @classmethod
+    def from_ascii(cls, bases, offsets, threads=8):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        h = C.c_void_p()
+        check(lib.lrb_reads_from_ascii(_ptr(bases), _ptr(offsets), len(offsets) - 1, int(threads), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_lengths(cls, lengths):
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        h = C.c_void_p()
+        check(lib.lrb_reads_from_lengths(_ptr(lengths), len(lengths), C.byref(h)))
+        return cls(h)
+
+    # -- accessors ------------------------------------------------------------------------------
+    n_reads = property(lambda self: int(self.view.n_reads))
+    n_blocks = property(lambda self: int(self.view.n_blocks))
+    n_tiles = property(lambda self: int(self.view.n_tiles))
+    total_bases = property(lambda self: int(self.view.total_bases))
+
+    def _arr(self, ptr, n):
+        if n == 0:
+            return np.zeros(0, dtype=np.uint32)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(n,))
+
+    codes = property(lambda self: self._arr(self.view.codes, 2 * self.n_blocks + 2))
+    valid = property(lambda self: self._arr(self.view.valid, self.n_blocks + 1))
+    read_len = property(lambda self: self._arr(self.view.read_len, self.n_reads))
+    read_blk = property(lambda self: self._arr(self.view.read_blk, self.n_reads + 1))
+    tile_read = property(lambda self: self._arr(self.view.tile_read, self.n_tiles))
+    tile_blk = property(lambda self: self._arr(self.view.tile_blk, self.n_tiles))
+
+    def unpack(self, i):
+        n = int(self.read_len[i])
+        buf = C.create_string_buffer(max(n, 1))
+        check(lib.lrb_reads_unpack(self._h, i, buf, n))
+        return buf.raw[:n]
+
+    def close(self):
+        if self._h:
+            lib.lrb_reads_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU.  profile() is the seam-to-seam call: host buffers in, host buffers out."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib.lrb_ctx_create(int(device), C.byref(self._h)))
+        self.device = device
+
+    def profile(self, reads, k=None, bin_size=None, bins=None, want_table=False, use_loaded_table=False, out=None):
+        """Returns dict(comp=[N,P] u32, hist=[N,bins] u32, sums=[N] u32, table=[2^30] u32) for the requested parts.
+        `out` may carry preallocated (ideally page-locked) arrays under the same keys."""
+        n = reads.n_reads
+        out = dict(out or {})
+        comp = hist = sums = table = None
+        if k is not None:
+            comp = out.get("comp")
+            if comp is None:
+                comp = np.zeros((n, COMP_WIDTH[k]), dtype=np.uint32)
+        if bins is not None:
+            hist = out.get("hist")
+            if hist is None:
+                hist = np.zeros((n, bins), dtype=np.uint32)
+            sums = out.get("sums")
+            if sums is None:
+                sums = np.zeros(n, dtype=np.uint32)
+        if want_table:
+            table = out.get("table")
+            if table is None:
+                table = np.empty(_lib.TABLE_ENTRIES, dtype=np.uint32)
+        check(lib.lrb_profile_host(self._h, reads._h, int(k or 0), int(bin_size or 1), int(bins or 1),
+                                   _ptr(comp) if comp is not None else None, _ptr(hist) if hist is not None else None,
+                                   _ptr(sums) if sums is not None else None, _ptr(table) if table is not None else None,
+                                   1 if use_loaded_table else 0))
+        return {"comp": comp, "hist": hist, "sums": sums, "table": table}
+
+    def timings(self):
+        ms = (C.c_float * 7)()
+        check(lib.lrb_ctx_last_timings(self._h, ms))
+        return dict(zip(("h2d", "composition", "count", "mirror", "search", "d2h", "total"), [float(x) for x in ms]))
+
+    def table_load(self, path):
+        check(lib.lrb_ctx_table_load(self._h, str(path).encode()))
+
+    def table_save(self, path):
+        check(lib.lrb_ctx_table_save(self._h, str(path).encode()))
+
+    def close(self):
+        if self._h:
+            lib.lrb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint32):
+    """numpy array over cudaHostAlloc memory (freed when the array's base object dies)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = lib.lrb_pinned_alloc(max(n, 16))
+    if not p:
+        raise _lib.LrbError(_lib.LRB_ECUDA, _lib.last_error())
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            lib.lrb_pinned_free(self.p)
+
+    owner = _Owner(p)
+    buf = (C.c_uint8 * max(n, 16)).from_address(p)
+    buf._owner = owner
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+# ---- device-pointer level over torch tensors -------------------------------------------------------
+
+class DeviceReads:
+    """The packed read set resident in HBM as torch tensors (int32 views of the u32 words)."""
+
+    def __init__(self, reads, device, upload=True):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.n_reads, self.n_blocks, self.n_tiles, self.total_bases = reads.n_reads, reads.n_blocks, reads.n_tiles, reads.total_bases
+
+        def up(a, n, fill=True):
+            t = torch.zeros(max(n, 1), dtype=torch.int32, device=self.device)
+            if fill and len(a):
+                t[:len(a)].copy_(torch.from_numpy(a.view(np.int32)))
+            return t
+
+        self.codes = up(reads.codes, 2 * self.n_blocks + 2, upload)
+        self.valid = up(reads.valid, self.n_blocks + 1, upload)
+        self.read_len = up(reads.read_len, self.n_reads)
+        self.read_blk = up(reads.read_blk, self.n_reads + 1)
+        self.tile_read = up(reads.tile_read, self.n_tiles)
+        self.tile_blk = up(reads.tile_blk, self.n_tiles)
+        self.tile_read_host = np.array(reads.tile_read, copy=True)
+        self.view = ReadsView(self.n_reads, self.n_blocks, self.n_tiles, self.total_bases, self.codes.data_ptr(),
+                              self.valid.data_ptr(), self.read_len.data_ptr(), self.read_blk.data_ptr(),
+                              self.tile_read.data_ptr(), self.tile_blk.data_ptr())
+
+    def download_into(self, reads):
+        """Copy the device stream back into the host buffers of `reads` (same layout)."""
+        torch = self.torch
+        torch.from_numpy(reads.codes.view(np.int32)).copy_(self.codes[:2 * self.n_blocks + 2])
+        torch.from_numpy(reads.valid.view(np.int32)).copy_(self.valid[:self.n_blocks + 1])
+
+    def tile_range_for_reads(self, read_lo, read_hi):
+        lo = int(np.searchsorted(self.tile_read_host, read_lo, side="left"))
+        hi = int(np.searchsorted(self.tile_read_host, read_hi, side="left"))
+        return lo, hi
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dev_composition(dr, k, counts, tile_lo=0, tile_hi=None):
+    check(lib.lrb_dev_composition(C.byref(dr.view), k, C.c_void_p(counts.data_ptr()), tile_lo,
+                                  dr.n_tiles if tile_hi is None else tile_hi, _stream()))
+
+
+def dev_count(dr, table, blk_lo=0, blk_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTRIES):
+    check(lib.lrb_dev_count(C.byref(dr.view), C.c_void_p(table.data_ptr()), blk_lo, dr.n_blocks if blk_hi is None else blk_hi,
+                            key_lo, min(key_hi, _lib.TABLE_ENTRIES), _stream()))
+
+
+def dev_mirror(table):
+    check(lib.lrb_dev_mirror(C.c_void_p(table.data_ptr()), _stream()))
+
+
+def dev_search(dr, table, bin_size, bins, hist, sums, tile_lo=0, tile_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTRIES):
+    check(lib.lrb_dev_search(C.byref(dr.view), C.c_void_p(table.data_ptr()), bin_size, bins, C.c_void_p(hist.data_ptr()),
+                             C.c_void_p(sums.data_ptr()), tile_lo, dr.n_tiles if tile_hi is None else tile_hi, key_lo,
+                             min(key_hi, _lib.TABLE_ENTRIES), _stream()))
+
+
+def dev_format_composition(counts, read_len, n_reads, k, text):
+    check(lib.lrb_dev_format_composition(C.c_void_p(counts.data_ptr()), C.c_void_p(read_len.data_ptr()), n_reads, k,
+                                         C.c_void_p(text.data_ptr()), _stream()))
+
+
+def dev_format_coverage(hist, sums, n_reads, bins, text):
+    check(lib.lrb_dev_format_coverage(C.c_void_p(hist.data_ptr()), C.c_void_p(sums.data_ptr()), n_reads, bins,
+                                      C.c_void_p(text.data_ptr()), _stream()))
+
+
+def kmer_lut(k):
+    lut = np.zeros(4 ** k, dtype=np.uint16)
+    width = lib.lrb_kmer_lut(k, _ptr(lut))
+    return lut, width

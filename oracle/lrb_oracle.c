@@ -72,8 +72,10 @@ void orc_composition(const char* seq, size_t len, int k, const uint32_t* lut, in
 
 static int orc_is_acgt(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
 
-/* kmer_utils.h:114-156 */
-void orc_count_15mers(const char* seq, size_t len, uint32_t* table) {
+/* kmer_utils.h:114-156, with the k-mer length as a parameter (the reference fixes k = 15, mask 4^15-1;
+ * other odd k are only used by tests of the multi-GPU plumbing, where a 4 GiB table would be wasteful). */
+void orc_count_kmers_k(const char* seq, size_t len, int k, uint32_t* table) {
+    const uint64_t mask = (1ull << (2 * k)) - 1;
     uint64_t val = 0;
     long run = 0;
     for (size_t i = 0; i < len; ++i) {
@@ -82,16 +84,18 @@ void orc_count_15mers(const char* seq, size_t len, uint32_t* table) {
             run = 0;
             continue;
         }
-        val = (val << 2) & ORC_MASK15;
+        val = (val << 2) & mask;
         val += (uint64_t)((seq[i] >> 1) & 3);
         run++;
-        if (run == 15) {
+        if (run == k) {
             run--;
-            table[val] += 1u;                    /* :139-145 CAS loop == +1 mod 2^32 */
-            table[orc_revcomp(val, 15)] += 1u;   /* :148-153 */
+            table[val] += 1u;                   /* :139-145 CAS loop == +1 mod 2^32 */
+            table[orc_revcomp(val, k)] += 1u;   /* :148-153 */
         }
     }
 }
+
+void orc_count_15mers(const char* seq, size_t len, uint32_t* table) { orc_count_kmers_k(seq, len, 15, table); }
 
 /* kmer_utils.h:54-69 */
 int orc_bucket(uint32_t count_u32, long bin_size, int bins) {
@@ -103,9 +107,10 @@ int orc_bucket(uint32_t count_u32, long bin_size, int bins) {
     return bins - 1;
 }
 
-/* kmer_utils.h:24-87 */
-void orc_coverage(const char* seq, size_t len, const uint32_t* table, long bin_size, int bins,
-                  uint64_t* raw, uint64_t* sum_out, double* vec) {
+/* kmer_utils.h:24-87, k-mer length as a parameter (reference: 15) */
+void orc_coverage_k(const char* seq, size_t len, int k, const uint32_t* table, long bin_size, int bins,
+                    uint64_t* raw, uint64_t* sum_out, double* vec) {
+    const uint64_t mask = (1ull << (2 * k)) - 1;
     uint64_t val = 0, sum = 0;
     long run = 0;
     for (int i = 0; i < bins; ++i) raw[i] = 0;
@@ -115,10 +120,10 @@ void orc_coverage(const char* seq, size_t len, const uint32_t* table, long bin_s
             run = 0;
             continue;
         }
-        val = (val << 2) & ORC_MASK15;
+        val = (val << 2) & mask;
         val += (uint64_t)((seq[i] >> 1) & 3);
         run++;
-        if (run == 15) {
+        if (run == k) {
             run--;
             raw[orc_bucket(table[val], bin_size, bins)]++;
             sum++;
@@ -134,6 +139,11 @@ void orc_coverage(const char* seq, size_t len, const uint32_t* table, long bin_s
             }
         }
     }
+}
+
+void orc_coverage(const char* seq, size_t len, const uint32_t* table, long bin_size, int bins,
+                  uint64_t* raw, uint64_t* sum_out, double* vec) {
+    orc_coverage_k(seq, len, 15, table, bin_size, bins, raw, sum_out, vec);
 }
 
 /* ---- record stream (kseq.h restated over an in-memory byte array) ---------------------------- */

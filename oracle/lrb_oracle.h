@@ -40,6 +40,12 @@ void orc_count_15mers(const char* seq, size_t len, uint32_t* table);
 void orc_coverage(const char* seq, size_t len, const uint32_t* table, long bin_size, int bins,
                   uint64_t* raw, uint64_t* sum, double* vec);
 
+/* The same two functions with the k-mer length as a parameter (k = 15 is the reference; other odd k serve
+ * the CPU tests of the multi-GPU plumbing). table has 4^k entries. */
+void orc_count_kmers_k(const char* seq, size_t len, int k, uint32_t* table);
+void orc_coverage_k(const char* seq, size_t len, int k, const uint32_t* table, long bin_size, int bins,
+                    uint64_t* raw, uint64_t* sum, double* vec);
+
 /* Bucket rule alone (kmer_utils.h:54-69): global count -> histogram bin. */
 int orc_bucket(uint32_t count, long bin_size, int bins);
 

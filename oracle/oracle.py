@@ -54,6 +54,10 @@ def lib():
         L.orc_count_15mers.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
         L.orc_coverage.restype = None
         L.orc_coverage.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_count_kmers_k.restype = None
+        L.orc_count_kmers_k.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p]
+        L.orc_coverage_k.restype = None
+        L.orc_coverage_k.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bucket.restype = C.c_int
         L.orc_bucket.argtypes = [C.c_uint32, C.c_long, C.c_int]
         L.orc_reads_load.restype = C.c_int
@@ -139,6 +143,27 @@ class Table:
             self.close()
         except Exception:
             pass
+
+
+class SmallTable:
+    """4^k-entry table for odd k < 15 (tests of the multi-GPU plumbing only; the reference fixes k = 15)."""
+
+    def __init__(self, k):
+        self.k = k
+        self.array = np.zeros(4 ** k, dtype=np.uint32)
+
+    def count(self, seq):
+        s = _as_bytes(seq)
+        lib().orc_count_kmers_k(s, len(s), self.k, self.array.ctypes.data)
+
+    def coverage(self, seq, bin_size, bins):
+        s = _as_bytes(seq)
+        raw = np.zeros(bins, dtype=np.uint64)
+        vec = np.zeros(bins, dtype=np.float64)
+        total = C.c_uint64(0)
+        lib().orc_coverage_k(s, len(s), self.k, self.array.ctypes.data, bin_size, bins, raw.ctypes.data, C.byref(total),
+                             vec.ctypes.data)
+        return raw, total.value, vec
 
 
 def bucket(count, bin_size, bins):

@@ -1,0 +1,139 @@
+"""world_size-2 gloo test of the multi-GPU decomposition logic (lrbinner_b200/dist.py) on the CPU.
+
+The per-GPU work is injected: an oracle-backed engine (tests only) stands in for the CUDA kernels, so what
+is checked here is the sharding (key ranges, read ranges, padding), the collectives and their order — for
+all three plans, against the single-process oracle result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, ROOT
+
+K, BS, BC = 3, 10, 8
+KT = 9   # k-mer length of the table in this test: 4^9 entries instead of 4^15, same plumbing (see OracleEngine)
+
+
+class OracleEngine:
+    """Test stand-in for CudaEngine: same interface, results from oracle/ (CPU restatement).  It runs the
+    table passes with 9-mers (oracle.SmallTable, the reference's rolling/reset/both-strands rule with k as a
+    parameter) so that the collectives move 1 MiB instead of 4 GiB; the k = 15 arithmetic itself is pinned
+    elsewhere (tests/test_oracle_pins.py, tests/test_host_cpu.py, tests/test_gpu_parity.py)."""
+
+    def __init__(self, seqs):
+        from oracle import oracle
+        self.o = oracle
+        self.seqs = seqs
+        self.n_reads = len(seqs)
+        self.table_entries = 4 ** KT
+        self._sparse = {}
+
+    def zeros(self, shape):
+        return torch.zeros(shape, dtype=torch.int32)
+
+    def _read_keys(self, i):
+        """middle-bit-clear keys of read i with their window multiplicity (= what the count kernel increments)."""
+        if i not in self._sparse:
+            t = self.o.SmallTable(KT)
+            t.count(self.seqs[i])
+            keys = np.flatnonzero(t.array)
+            keys = keys[(keys & (1 << KT)) == 0]
+            self._sparse[i] = (keys, t.array[keys].astype(np.int64))
+        return self._sparse[i]
+
+    def composition(self, k, comp, lo, hi):
+        for i in range(lo, hi):
+            comp[i] += torch.from_numpy(self.o.composition(self.seqs[i], k)[0].astype(np.int32))
+
+    def count(self, table, klo, khi, lo, hi):
+        tv = table.numpy().view(np.uint32)
+        for i in range(lo, hi):
+            keys, mult = self._read_keys(i)
+            sel = (keys >= klo) & (keys < khi)
+            np.add.at(tv, keys[sel], mult[sel].astype(np.uint32))
+
+    def mirror(self, table):
+        tv = table.numpy().view(np.uint32)
+        nz = np.flatnonzero(tv)
+        for x in nz[(nz & (1 << KT)) == 0]:
+            tv[self.o.revcomp(int(x), KT)] = tv[x]
+
+    def search(self, table, bs, bc, hist, sums, lo, hi, klo, khi):
+        tv = table.numpy().view(np.uint32)
+        for i in range(lo, hi):
+            keys, mult = self._read_keys(i)
+            sel = (keys >= klo) & (keys < khi)
+            for x, m in zip(keys[sel], mult[sel]):
+                hist[i, self.o.bucket(int(tv[x]), bs, bc)] += int(m)
+                sums[i] += int(m)
+
+
+def _worker(rank, world, port, plan, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from lrbinner_b200 import dist as lrb_dist
+    from oracle import oracle
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seqs, _ = oracle.load_reads(os.path.join(GOLDEN, "g06_community.fa"))
+    seqs = seqs[:41]                                   # odd count: exercises the padded last chunk
+    eng = OracleEngine(seqs)
+    res = lrb_dist.profile_distributed(eng, K, BS, BC, plan)
+    lo, hi = res["own"]
+    q.put((rank, lo, hi, res["comp"].numpy().copy(), res["hist"].numpy().copy(), res["sums"].numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("plan", ["keyshard_rs", "keyshard_ag", "readshard_ar"])
+def test_two_rank_plans_match_single_process_oracle(plan):
+    from oracle import oracle
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, plan, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    seqs, _ = oracle.load_reads(os.path.join(GOLDEN, "g06_community.fa"))
+    seqs = seqs[:41]
+    table = oracle.SmallTable(KT)
+    for s in seqs:
+        table.count(s)
+    covered = []
+    for rank, lo, hi, comp, hist, sums in sorted(got):
+        covered += list(range(lo, hi))
+        assert comp.shape[0] == hist.shape[0] == sums.shape[0] == hi - lo
+        for row, i in enumerate(range(lo, hi)):
+            assert np.array_equal(comp[row].astype(np.uint32), oracle.composition(seqs[i], K)[0].astype(np.uint32)), (plan, i)
+            raw, total, _ = table.coverage(seqs[i], BS, BC)
+            assert np.array_equal(hist[row].astype(np.uint32), raw.astype(np.uint32)) and int(sums[row]) == total, (plan, i)
+    assert covered == list(range(len(seqs)))
+
+
+def test_shard_arithmetic():
+    from lrbinner_b200 import dist as d
+    for n in (0, 1, 7, 8, 41, 1000):
+        for w in (1, 2, 3, 4, 8):
+            spans = [d.own_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(hi - lo <= d.chunk_size(n, w) for lo, hi in spans)
+    for w in (1, 2, 4, 8):
+        ks = [d.key_range(w, r) for r in range(w)]
+        assert ks[0][0] == 0 and ks[-1][1] == 2 ** 30 == d.TABLE_ENTRIES and all(a[1] == b[0] for a, b in zip(ks, ks[1:]))

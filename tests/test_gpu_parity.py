@@ -1,0 +1,331 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against the oracle, the golden files
+of the reference tools, and size-independent properties at BASELINE.json's full sizes.
+
+Bar: bit-exact for every integer result (15-mer table, coverage histograms, raw composition counts)
+and byte-exact for the text files; normalised values are derived from the integers by the exact %f
+formatter (tests/test_host_cpu.py), so they match to the last printed digit (<= 1e-6 relative is the
+stated tolerance, BASELINE.json north_star).
+"""
+import ctypes as C
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from conftest import COV_PARAMS, GOLDEN, golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from oracle import oracle  # noqa: E402
+from lrbinner_b200 import _lib, runners_utils  # noqa: E402
+from lrbinner_b200.profile import (COMP_WIDTH, Context, DeviceReads, PackedReads, dev_composition, dev_count,  # noqa: E402
+                                   dev_format_composition, dev_format_coverage, dev_mirror, dev_search, _ptr)
+from lrbinner_b200.synth import CONFIGS, SynthSpec, write_fasta  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _gz(path):
+    with gzip.open(path, "rb") as f:
+        return f.read()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _oracle_profile(seqs, k_list, cov_params):
+    table = oracle.Table()
+    for s in seqs:
+        table.count(s)
+    comp = {k: np.stack([oracle.composition(s, k)[0] for s in seqs]).astype(np.uint32) if seqs else np.zeros((0, COMP_WIDTH[k]), np.uint32)
+            for k in k_list}
+    cov = {}
+    for bs, bc in cov_params:
+        rows = [table.coverage(s, bs, bc) for s in seqs]
+        if rows:
+            cov[(bs, bc)] = (np.stack([r[0] for r in rows]).astype(np.uint32), np.array([r[1] for r in rows], dtype=np.uint32))
+        else:
+            cov[(bs, bc)] = (np.zeros((0, bc), np.uint32), np.zeros(0, np.uint32))
+    return comp, table, cov
+
+
+def _assert_table_equal(got, want):
+    nz = np.flatnonzero(want)
+    assert np.array_equal(np.flatnonzero(got), nz)
+    assert np.array_equal(got[nz], want[nz])
+
+
+# ---- golden files of the reference tools, through the file-level drop-ins -------------------------------------
+
+@pytest.mark.parametrize("name", golden_inputs())
+def test_dropin_text_files_byte_identical(name, tmp_path, ctx):
+    stem = name.split(".")[0]
+    src = os.path.join(GOLDEN, name)
+    out = str(tmp_path)
+    for k in (3, 4, 5):
+        runners_utils.run_kmers(src, out, k, 4)
+        assert open(f"{out}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, f"{stem}.com_k{k}.txt.gz")), (name, k)
+    # buffer-level table (the 4 GiB file path is exercised once below) + every coverage parameter pair
+    pr = PackedReads.from_file(src, threads=2)
+    gold = np.load(os.path.join(GOLDEN, f"{stem}.table.npz"))
+    res = ctx.profile(pr, bin_size=COV_PARAMS[0][0], bins=COV_PARAMS[0][1], want_table=True)
+    keys = gold["keys"].astype(np.int64)
+    assert np.array_equal(np.flatnonzero(res["table"]), keys) and np.array_equal(res["table"][keys], gold["counts"])
+    for bs, bc in COV_PARAMS:
+        r = ctx.profile(pr, bin_size=bs, bins=bc, use_loaded_table=True)
+        path = f"{out}/cov"
+        assert _lib.lib.lrb_write_coverage_txt(path.encode(), _ptr(r["hist"]), _ptr(r["sums"]), pr.n_reads, bc, 2) == 0
+        assert open(path, "rb").read() == _gz(os.path.join(GOLDEN, f"{stem}.cov_bs{bs}_bc{bc}.txt.gz")), (name, bs, bc)
+
+
+def test_dropin_three_stage_sequence_and_fused(tmp_path):
+    """run_kmers -> run_15mer_counts -> run_15mer_vecs exactly as pipelines.py:269-306 calls them,
+    then the fused run_profile; both must leave the reference tools' bytes on disk."""
+    import hashlib
+    src = os.path.join(GOLDEN, "g06_community.fa")
+    out = str(tmp_path / "o1")
+    runners_utils.run_kmers(src, out, 3, 4)
+    runners_utils.run_15mer_counts(src, out, 4)
+    runners_utils.run_15mer_vecs(src, out, 32, 10, 4)
+    gold = np.load(os.path.join(GOLDEN, "g06_community.table.npz"))
+    tfile = f"{out}/profiles/15mers-counts"
+    assert os.path.getsize(tfile) == int(gold["file_bytes"]) == 8 + 4 * 2 ** 30
+    h = hashlib.sha256()
+    with open(tfile, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 24), b""):
+            h.update(blk)
+    assert h.hexdigest() == str(gold["sha256"])          # the whole 4 GiB file, bit for bit
+    assert open(f"{out}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.com_k3.txt.gz"))
+    assert open(f"{out}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.cov_bs32_bc10.txt.gz"))
+    # resume-style: only stage 2_1 re-run with other -bs/-bc from the stored table
+    runners_utils.run_15mer_vecs(src, out, 10, 8, 4)
+    assert open(f"{out}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.cov_bs10_bc8.txt.gz"))
+    os.remove(tfile)
+    out2 = str(tmp_path / "o2")
+    runners_utils.run_profile(src, out2, 5, 10, 32, 4, write_table=False, write_npy=True)
+    assert open(f"{out2}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.com_k5.txt.gz"))
+    assert open(f"{out2}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.cov_bs10_bc32.txt.gz"))
+    want = np.array([np.array(list(map(float, line.strip().split()))) for line in open(f"{out2}/profiles/cov_profs") if len(line.strip()) > 0])
+    assert np.array_equal(np.load(f"{out2}/profiles/cov_profs.npy"), want)
+
+
+def test_missing_input_gives_empty_outputs_like_the_tools(tmp_path):
+    out = str(tmp_path)
+    runners_utils.run_kmers(str(tmp_path / "nope.fa"), out, 3, 2)
+    assert os.path.getsize(f"{out}/profiles/com_profs") == 0
+    with pytest.raises(SystemExit):
+        runners_utils.run_15mer_vecs(str(tmp_path / "nope.fa"), out, 32, 10, 2)   # no table file -> check_proc -> sys.exit
+
+
+def test_bad_parameters_are_errors(ctx):
+    pr = PackedReads.from_sequences([b"ACGT" * 20])
+    for kw in (dict(k=6), dict(bin_size=0, bins=10), dict(bin_size=10, bins=0), dict(bin_size=10, bins=5000)):
+        with pytest.raises((_lib.LrbError, KeyError)):
+            ctx.profile(pr, **kw)
+
+
+# ---- seeded synthetic reads vs the oracle ---------------------------------------------------------------
+
+@pytest.mark.parametrize("seed,n,lengths,kw", [
+    (1, 1500, "gamma5k", dict(n_rate=1e-3, lowercase_frac=0.01, edge_lengths=True)),
+    (2, 400, "longtail", dict(n_rate=1e-4, edge_lengths=True)),
+    (3, 600, "hifi15k", dict(errors="hifi")),
+])
+def test_synthetic_reads_bit_exact_vs_oracle(ctx, seed, n, lengths, kw):
+    spec = SynthSpec(n, lengths=lengths, seed=seed, scale=0.02, **kw)
+    seqs = spec.host_sequences()
+    pr = spec.host_packed(threads=4)
+    cov_params = [(32, 10), (10, 32), (3, 7)]
+    comp, table, cov = _oracle_profile(seqs, (3, 4, 5), cov_params)
+    first = True
+    for k in (3, 4, 5):
+        bs, bc = cov_params[0]
+        res = ctx.profile(pr, k=k, bin_size=bs, bins=bc, want_table=first)
+        assert np.array_equal(res["comp"], comp[k]), k
+        assert np.array_equal(res["hist"], cov[(bs, bc)][0]) and np.array_equal(res["sums"], cov[(bs, bc)][1])
+        if first:
+            _assert_table_equal(res["table"], table.array)
+        first = False
+    for bs, bc in cov_params[1:]:
+        res = ctx.profile(pr, bin_size=bs, bins=bc, use_loaded_table=True)
+        assert np.array_equal(res["hist"], cov[(bs, bc)][0]) and np.array_equal(res["sums"], cov[(bs, bc)][1]), (bs, bc)
+    table.close()
+
+
+def test_empty_and_tiny_read_sets(ctx):
+    for seqs in ([], [b""], [b"", b"A", b"AC"], [b"ACGTACGTACGTAC"], [b"ACGTACGTACGTACG"], [b"N" * 100], [b"acgt" * 30]):
+        pr = PackedReads.from_sequences(seqs)
+        res = ctx.profile(pr, k=3, bin_size=10, bins=8, want_table=True)
+        comp, table, cov = _oracle_profile(seqs, (3,), [(10, 8)])
+        assert np.array_equal(res["comp"], comp[3])
+        assert np.array_equal(res["hist"].reshape(-1), cov[(10, 8)][0].reshape(-1)) and np.array_equal(res["sums"], cov[(10, 8)][1])
+        _assert_table_equal(res["table"], table.array)
+        table.close()
+
+
+def test_u32_wraparound_is_modular(ctx):
+    """No saturation in the reference (kmer_utils.h:139-153: +1 mod 2^32): preload a table near the top."""
+    seqs = [b"ACGTTGCAAGGCTTACGATC" * 5] * 3
+    pr = PackedReads.from_sequences(seqs)
+    dr = DeviceReads(pr, DEV)
+    table = torch.full((2 ** 30,), -2, dtype=torch.int32, device=DEV)   # 0xFFFFFFFE everywhere
+    dev_count(dr, table)
+    torch.cuda.synchronize()
+    want = oracle.Table()
+    for s in seqs:
+        want.count(s)
+    keys = np.flatnonzero(want.array)
+    canon = keys[(keys & 0x8000) == 0]
+    got = table[torch.from_numpy(canon.astype(np.int64)).to(DEV)].cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, (want.array[canon].astype(np.uint64) + 0xFFFFFFFE).astype(np.uint64) % (1 << 32))
+    want.close()
+
+
+# ---- device-level pieces -------------------------------------------------------------------------------
+
+def test_device_synth_and_pack_match_host():
+    spec = SynthSpec(3000, seed=9, n_rate=1e-3, lowercase_frac=0.02, edge_lengths=True, scale=0.02)
+    host = spec.host_packed(threads=4)
+    dr, layout = spec.device_reads(DEV)
+    assert np.array_equal(dr.codes.cpu().numpy().view(np.uint32)[:2 * host.n_blocks + 2], host.codes)
+    assert np.array_equal(dr.valid.cpu().numpy().view(np.uint32)[:host.n_blocks + 1], host.valid)
+    # device packer (ASCII in HBM -> packed) against the host packer
+    bases, offsets = spec.host_ascii()
+    d2 = DeviceReads(layout, DEV, upload=False)
+    db = torch.from_numpy(bases).to(DEV)
+    do = torch.from_numpy(offsets.view(np.int64)).to(DEV)
+    _lib.check(_lib.lib.lrb_dev_pack_ascii(C.byref(d2.view), C.c_void_p(db.data_ptr()), C.c_void_p(do.data_ptr()),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert np.array_equal(d2.codes.cpu().numpy().view(np.uint32)[:2 * host.n_blocks + 2], host.codes)
+    assert np.array_equal(d2.valid.cpu().numpy().view(np.uint32)[:host.n_blocks + 1], host.valid)
+
+
+def test_device_text_epilogue_matches_host_writer(tmp_path, ctx):
+    spec = SynthSpec(700, seed=4, n_rate=1e-3, edge_lengths=True, scale=0.02)
+    pr = spec.host_packed()
+    n = pr.n_reads
+    for k, (bs, bc) in ((3, (32, 10)), (4, (10, 32)), (5, (1, 5))):
+        res = ctx.profile(pr, k=k, bin_size=bs, bins=bc)
+        P = COMP_WIDTH[k]
+        rl = np.array(pr.read_len)
+        path = str(tmp_path / "t")
+        assert _lib.lib.lrb_write_composition_txt(path.encode(), _ptr(res["comp"]), _ptr(rl), n, k, 2) == 0
+        text = torch.zeros(n * (9 * P + 1), dtype=torch.uint8, device=DEV)
+        dev_format_composition(torch.from_numpy(res["comp"].view(np.int32)).to(DEV), torch.from_numpy(rl.view(np.int32)).to(DEV), n, k, text)
+        assert text.cpu().numpy().tobytes() == open(path, "rb").read()
+        assert _lib.lib.lrb_write_coverage_txt(path.encode(), _ptr(res["hist"]), _ptr(res["sums"]), n, bc, 2) == 0
+        text = torch.zeros(n * 9 * bc, dtype=torch.uint8, device=DEV)
+        dev_format_coverage(torch.from_numpy(res["hist"].view(np.int32)).to(DEV), torch.from_numpy(res["sums"].view(np.int32)).to(DEV), n, bc, text)
+        assert text.cpu().numpy().tobytes() == open(path, "rb").read()
+
+
+def test_key_sharded_count_and_search_sum_to_whole():
+    """The multi-GPU decomposition on one device: 4 key shards counted separately and partial histograms
+    summed (plan A), and read-sharded search on the merged table (plan B), both equal the single pass."""
+    spec = SynthSpec(4000, seed=12, n_rate=1e-4, edge_lengths=True, scale=0.05)
+    pr = spec.host_packed()
+    dr = DeviceReads(pr, DEV)
+    n, bs, bc = pr.n_reads, 32, 10
+    whole = torch.zeros(2 ** 30, dtype=torch.int32, device=DEV)
+    dev_count(dr, whole)
+    parts = torch.zeros(2 ** 30, dtype=torch.int32, device=DEV)
+    bounds = [0, 2 ** 28, 2 ** 29, 3 * 2 ** 28, 2 ** 30]
+    hist_a = torch.zeros((n, bc), dtype=torch.int32, device=DEV)
+    sums_a = torch.zeros(n, dtype=torch.int32, device=DEV)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        dev_count(dr, parts, key_lo=lo, key_hi=hi)
+        dev_search(dr, parts, bs, bc, hist_a, sums_a, key_lo=lo, key_hi=hi)      # plan A: partial histograms accumulate
+    assert torch.equal(whole, parts)
+    dev_mirror(whole)
+    hist_w = torch.zeros((n, bc), dtype=torch.int32, device=DEV)
+    sums_w = torch.zeros(n, dtype=torch.int32, device=DEV)
+    dev_search(dr, whole, bs, bc, hist_w, sums_w)
+    assert torch.equal(hist_w, hist_a) and torch.equal(sums_w, sums_a)
+    # plan B: read shards (tile ranges) against the full table
+    hist_b = torch.zeros((n, bc), dtype=torch.int32, device=DEV)
+    sums_b = torch.zeros(n, dtype=torch.int32, device=DEV)
+    cuts = [0, n // 3, n // 2, n]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        tlo, thi = dr.tile_range_for_reads(lo, hi)
+        dev_search(dr, whole, bs, bc, hist_b, sums_b, tile_lo=tlo, tile_hi=thi)
+    assert torch.equal(hist_w, hist_b) and torch.equal(sums_w, sums_b)
+    # block-range sharded count (data-parallel over the stream) also sums to the whole
+    parts.zero_()
+    nb = pr.n_blocks
+    for lo, hi in ((0, nb // 5), (nb // 5, nb // 2 + 1), (nb // 2 + 1, nb)):
+        dev_count(dr, parts, blk_lo=lo, blk_hi=hi)
+    dev_mirror(parts)
+    assert torch.equal(whole, parts)
+
+
+# ---- full-size properties (BASELINE.json configs) ---------------------------------------------------------
+
+def _full_size_properties(name, subsample=200):
+    cfg = CONFIGS[name]
+    spec = SynthSpec(cfg["n_reads"], lengths=cfg["lengths"], errors=cfg["errors"], seed=cfg["seed"])
+    dr, layout = spec.device_reads(DEV)
+    n, k, bs, bc = spec.n_reads, cfg["k"], 32, 10
+    P = COMP_WIDTH[k]
+    lens = torch.from_numpy(spec.lengths.astype(np.int64)).to(DEV)
+    comp = torch.zeros((n, P), dtype=torch.int32, device=DEV)
+    dev_composition(dr, k, comp)
+    assert torch.equal(comp.sum(dim=1, dtype=torch.int64), (lens - k + 1).clamp(min=0))       # every window counted once
+    table = torch.zeros(2 ** 30, dtype=torch.int32, device=DEV)
+    dev_count(dr, table)
+    nwin = (lens - 14).clamp(min=0)                                                            # all-ACGT reads
+    half = int((table.view(torch.int32).to(torch.int64) & 0xFFFFFFFF).sum().item())
+    assert half == int(nwin.sum().item())                                                      # one increment per window (canonical half)
+    dev_mirror(table)
+    total = 0
+    for lo in range(0, 2 ** 30, 2 ** 28):
+        total += int((table[lo:lo + 2 ** 28].to(torch.int64) & 0xFFFFFFFF).sum().item())
+    assert total == 2 * half                                                                   # table sum = 2 x valid windows
+    # T[x] == T[rc(x)]: mirroring again is a no-op (idempotence)
+    chk = int(table[::4099].to(torch.int64).sum().item())
+    dev_mirror(table)
+    assert chk == int(table[::4099].to(torch.int64).sum().item())
+    hist = torch.zeros((n, bc), dtype=torch.int32, device=DEV)
+    sums = torch.zeros(n, dtype=torch.int32, device=DEV)
+    dev_search(dr, table, bs, bc, hist, sums)
+    assert torch.equal(sums.to(torch.int64), nwin) and torch.equal(hist.sum(dim=1, dtype=torch.int64), nwin)
+    # spot-check reads against the oracle restricted to the sampled reads' own k-mers:
+    # composition needs only the read; coverage needs global counts, looked up from the device table
+    rng = np.random.default_rng(1)
+    pick = np.sort(rng.choice(n, size=subsample, replace=False))
+    dr.download_into(layout)
+    comp_h = comp[torch.from_numpy(pick).to(DEV)].cpu().numpy().view(np.uint32)
+    hist_h = hist[torch.from_numpy(pick).to(DEV)].cpu().numpy().view(np.uint32)
+    for row, i in enumerate(pick):
+        s = layout.unpack(int(i))
+        assert np.array_equal(comp_h[row], oracle.composition(s, k)[0].astype(np.uint32)), i
+        # 15-mer keys of this read via the oracle's own rolling code (a private table), then bucket the device counts
+        priv = oracle.Table()
+        priv.count(s)
+        keys = np.flatnonzero(priv.array)
+        mult = priv.array[keys]
+        priv.close()
+        fw = keys  # both strands present; forward windows = half of the total mass, bucket by device count
+        dev_counts = table[torch.from_numpy(fw.astype(np.int64)).to(DEV)].cpu().numpy().view(np.uint32)
+        want = np.zeros(bc, dtype=np.uint64)
+        for c, m_ in zip(dev_counts, mult):
+            want[oracle.bucket(int(c), bs, bc)] += int(m_)
+        assert np.array_equal(want, 2 * hist_h[row].astype(np.uint64)), i      # each window seen on both strands
+    del table, comp, hist
+
+
+def test_full_size_properties_config1():
+    _full_size_properties("cfg1_100k_5kb_k3")
+
+
+def test_full_size_properties_config2_headline():
+    _full_size_properties("cfg2_1M_5kb_ont_k4", subsample=100)
