@@ -106,6 +106,25 @@ int lrb_dev_mirror(uint32_t* table, void* stream);
 int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_size, int bins, uint32_t* hist,
                    uint32_t* sums, uint64_t tile_lo, uint64_t tile_hi, uint32_t key_lo, uint32_t key_hi, void* stream);
 
+/* L2-resident variant of count and/or search (csrc/partition.cu): the valid windows of blocks
+ * [blk_lo, blk_hi) whose bit-15-clear key lies in [key_lo, key_hi) are partitioned by key >> log2_bucket_keys
+ * into at most 64 buckets (key range must be bucket-aligned); then per bucket the keys are applied to the
+ * table slice while it is resident in L2.  do_count: table[key] += 1 (as lrb_dev_count; mirror separately).
+ * hist != NULL: search (as lrb_dev_search through table[bit-15-clear key]); with do_count the search of a
+ * bucket follows its count directly.  blk_read[n_blocks] = read index of every block (lrb_dev_fill_blk_read).
+ * Workspace: ws_keys / ws_rids hold ws_capacity u32 each (ws_rids may be NULL when hist is NULL);
+ * ws_small >= 192 u64.  Bit-identical to the direct kernels.  Synchronises `stream` once (region sizes). */
+int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_read, void* stream);
+int lrb_dev_table15_partitioned(const lrb_reads_view* dev, const uint32_t* blk_read, uint32_t* table, int do_count,
+                                long bin_size, int bins, uint32_t* hist, uint32_t* sums, uint64_t blk_lo,
+                                uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
+                                uint32_t* ws_keys, uint32_t* ws_rids, uint64_t ws_capacity,
+                                unsigned long long* ws_small, void* stream);
+
+/* cudaLimitMaxL2FetchGranularity for the current device (32, 64 or 128 bytes): the table passes are random
+ * 4-byte accesses, 32 avoids over-fetching neighbouring sectors from HBM. */
+int lrb_dev_set_l2_fetch_granularity(int bytes);
+
 /* Pack ASCII on the device: bases[] (device, concatenated) -> codes/valid of `dev` (layout prebuilt). */
 int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, const uint64_t* offsets, void* stream);
 

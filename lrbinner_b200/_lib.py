@@ -55,6 +55,10 @@ _SIG = {
     "lrb_dev_mirror": (C.c_int, [_P, _P]),
     "lrb_dev_search": (C.c_int, [C.POINTER(ReadsView), _P, C.c_long, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
                                  C.c_uint32, C.c_uint32, _P]),
+    "lrb_dev_fill_blk_read": (C.c_int, [C.POINTER(ReadsView), _P, _P]),
+    "lrb_dev_table15_partitioned": (C.c_int, [C.POINTER(ReadsView), _P, _P, C.c_int, C.c_long, C.c_int, _P, _P, C.c_uint64,
+                                              C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P, _P, C.c_uint64, _P, _P]),
+    "lrb_dev_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
     "lrb_dev_pack_ascii": (C.c_int, [C.POINTER(ReadsView), _P, _P, _P]),
     "lrb_dev_format_composition": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
     "lrb_dev_format_coverage": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),

@@ -40,6 +40,15 @@ void lrb_host_free(void* p, bool pinned) {
     else free(p);
 }
 
+// Random 4-byte table accesses over-fetch when L2 pulls more than one 32 B sector per miss from HBM
+// (ncu: 126 B of DRAM reads per gather at the default setting); 32 asks for single-sector fills.
+extern "C" int lrb_dev_set_l2_fetch_granularity(int bytes) {
+    if (bytes != 32 && bytes != 64 && bytes != 128) return lrb_set_error(LRB_EINVAL, "L2 fetch granularity must be 32, 64 or 128");
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+    if (e != cudaSuccess) return lrb_set_error(LRB_ECUDA, "cudaDeviceSetLimit(L2 fetch granularity) failed: %s", cudaGetErrorString(e));
+    return LRB_OK;
+}
+
 extern "C" void* lrb_pinned_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) {

@@ -120,7 +120,7 @@ class Context:
         if bins is not None:
             hist = out.get("hist")
             if hist is None:
-                hist = np.zeros((n, bins), dtype=np.uint32)
+                hist = np.zeros((n, max(int(bins), 1)), dtype=np.uint32)
             sums = out.get("sums")
             if sums is None:
                 sums = np.zeros(n, dtype=np.uint32)
@@ -128,7 +128,8 @@ class Context:
             table = out.get("table")
             if table is None:
                 table = np.empty(_lib.TABLE_ENTRIES, dtype=np.uint32)
-        check(lib.lrb_profile_host(self._h, reads._h, int(k or 0), int(bin_size or 1), int(bins or 1),
+        check(lib.lrb_profile_host(self._h, reads._h, int(k) if k is not None else 0,
+                                   int(bin_size) if bin_size is not None else 1, int(bins) if bins is not None else 1,
                                    _ptr(comp) if comp is not None else None, _ptr(hist) if hist is not None else None,
                                    _ptr(sums) if sums is not None else None, _ptr(table) if table is not None else None,
                                    1 if use_loaded_table else 0))
@@ -242,6 +243,29 @@ def dev_search(dr, table, bin_size, bins, hist, sums, tile_lo=0, tile_hi=None, k
     check(lib.lrb_dev_search(C.byref(dr.view), C.c_void_p(table.data_ptr()), bin_size, bins, C.c_void_p(hist.data_ptr()),
                              C.c_void_p(sums.data_ptr()), tile_lo, dr.n_tiles if tile_hi is None else tile_hi, key_lo,
                              min(key_hi, _lib.TABLE_ENTRIES), _stream()))
+
+
+class PartitionWorkspace:
+    """Scratch for the L2-resident table passes: (key, read) lists of up to `capacity` windows + the per-block read index."""
+
+    def __init__(self, dr, capacity=None, with_rids=True):
+        torch = dr.torch
+        self.capacity = int(capacity if capacity is not None else max(dr.total_bases, 1))
+        self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
+        self.rids = torch.empty(self.capacity, dtype=torch.int32, device=dr.device) if with_rids else None
+        self.small = torch.zeros(256, dtype=torch.int64, device=dr.device)
+        self.blk_read = torch.empty(max(dr.n_blocks, 1), dtype=torch.int32, device=dr.device)
+        check(lib.lrb_dev_fill_blk_read(C.byref(dr.view), C.c_void_p(self.blk_read.data_ptr()), _stream()))
+
+
+def dev_table15_partitioned(dr, ws, table, do_count=True, bin_size=1, bins=1, hist=None, sums=None, blk_lo=0, blk_hi=None,
+                            key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=25):
+    check(lib.lrb_dev_table15_partitioned(
+        C.byref(dr.view), C.c_void_p(ws.blk_read.data_ptr()), C.c_void_p(table.data_ptr()), 1 if do_count else 0, bin_size, bins,
+        C.c_void_p(hist.data_ptr()) if hist is not None else None, C.c_void_p(sums.data_ptr()) if sums is not None else None,
+        blk_lo, dr.n_blocks if blk_hi is None else blk_hi, key_lo, min(key_hi, _lib.TABLE_ENTRIES), log2_bucket_keys,
+        C.c_void_p(ws.keys.data_ptr()), C.c_void_p(ws.rids.data_ptr()) if ws.rids is not None else None, ws.capacity,
+        C.c_void_p(ws.small.data_ptr()), _stream()))
 
 
 def dev_format_composition(counts, read_len, n_reads, k, text):

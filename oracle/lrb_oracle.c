@@ -97,6 +97,31 @@ void orc_count_kmers_k(const char* seq, size_t len, int k, uint32_t* table) {
 
 void orc_count_15mers(const char* seq, size_t len, uint32_t* table) { orc_count_kmers_k(seq, len, 15, table); }
 
+/* The forward key of every valid window, in read order: the `val` the loops at kmer_utils.h:36-72 and
+ * :120-155 use as table index.  Returns the number of windows (out may be NULL to just count). */
+size_t orc_window_keys(const char* seq, size_t len, int k, uint32_t* out) {
+    const uint64_t mask = (1ull << (2 * k)) - 1;
+    uint64_t val = 0;
+    long run = 0;
+    size_t n = 0;
+    for (size_t i = 0; i < len; ++i) {
+        if (!orc_is_acgt(seq[i])) {
+            val = 0;
+            run = 0;
+            continue;
+        }
+        val = (val << 2) & mask;
+        val += (uint64_t)((seq[i] >> 1) & 3);
+        run++;
+        if (run == k) {
+            run--;
+            if (out) out[n] = (uint32_t)val;
+            n++;
+        }
+    }
+    return n;
+}
+
 /* kmer_utils.h:54-69 */
 int orc_bucket(uint32_t count_u32, long bin_size, int bins) {
     long count = (long)count_u32;

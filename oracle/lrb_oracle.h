@@ -46,6 +46,8 @@ void orc_count_kmers_k(const char* seq, size_t len, int k, uint32_t* table);
 void orc_coverage_k(const char* seq, size_t len, int k, const uint32_t* table, long bin_size, int bins,
                     uint64_t* raw, uint64_t* sum, double* vec);
 
+size_t orc_window_keys(const char* seq, size_t len, int k, uint32_t* out); /* forward key of each valid window */
+
 /* Bucket rule alone (kmer_utils.h:54-69): global count -> histogram bin. */
 int orc_bucket(uint32_t count, long bin_size, int bins);
 

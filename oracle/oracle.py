@@ -58,6 +58,8 @@ def lib():
         L.orc_count_kmers_k.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p]
         L.orc_coverage_k.restype = None
         L.orc_coverage_k.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_window_keys.restype = C.c_size_t
+        L.orc_window_keys.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p]
         L.orc_bucket.restype = C.c_int
         L.orc_bucket.argtypes = [C.c_uint32, C.c_long, C.c_int]
         L.orc_reads_load.restype = C.c_int
@@ -164,6 +166,14 @@ class SmallTable:
         lib().orc_coverage_k(s, len(s), self.k, self.array.ctypes.data, bin_size, bins, raw.ctypes.data, C.byref(total),
                              vec.ctypes.data)
         return raw, total.value, vec
+
+
+def window_keys(seq, k=15):
+    """Forward table index of every valid k-mer window of the read, in order (kmer_utils.h:36-72)."""
+    s = _as_bytes(seq)
+    out = np.zeros(max(len(s), 1), dtype=np.uint32)
+    n = lib().orc_window_keys(s, len(s), k, out.ctypes.data)
+    return out[:n]
 
 
 def bucket(count, bin_size, bins):

@@ -23,8 +23,9 @@ if not torch.cuda.is_available():
 
 from oracle import oracle  # noqa: E402
 from lrbinner_b200 import _lib, runners_utils  # noqa: E402
-from lrbinner_b200.profile import (COMP_WIDTH, Context, DeviceReads, PackedReads, dev_composition, dev_count,  # noqa: E402
-                                   dev_format_composition, dev_format_coverage, dev_mirror, dev_search, _ptr)
+from lrbinner_b200.profile import (COMP_WIDTH, Context, DeviceReads, PackedReads, PartitionWorkspace, dev_composition,  # noqa: E402
+                                   dev_count, dev_format_composition, dev_format_coverage, dev_mirror, dev_search,
+                                   dev_table15_partitioned, _ptr)
 from lrbinner_b200.synth import CONFIGS, SynthSpec, write_fasta  # noqa: E402
 
 DEV = "cuda:0"
@@ -268,6 +269,49 @@ def test_key_sharded_count_and_search_sum_to_whole():
     assert torch.equal(whole, parts)
 
 
+def test_partitioned_l2_resident_passes_equal_direct_kernels():
+    """csrc/partition.cu (key-partitioned, L2-resident count + search) against the direct kernels: fused,
+    count-only, search-only, key-sharded and block-range-sharded, for several bucket sizes."""
+    spec = SynthSpec(6000, seed=21, n_rate=1e-3, lowercase_frac=0.01, edge_lengths=True, scale=0.05)
+    pr = spec.host_packed()
+    dr = DeviceReads(pr, DEV)
+    n, bs, bc = pr.n_reads, 32, 10
+    z = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=DEV)
+    table_d, hist_d, sums_d = z(2 ** 30), z(n, bc), z(n)
+    dev_count(dr, table_d)
+    dev_search(dr, table_d, bs, bc, hist_d, sums_d, key_lo=0, key_hi=2 ** 29)      # canonical-key lookups on the unmirrored table
+    dev_search(dr, table_d, bs, bc, hist_d, sums_d, key_lo=2 ** 29, key_hi=2 ** 30)
+    ws = PartitionWorkspace(dr)
+    blk = np.array(pr.read_blk)
+    assert np.array_equal(ws.blk_read.cpu().numpy().view(np.uint32)[:pr.n_blocks], np.repeat(np.arange(n, dtype=np.uint32), np.diff(blk)))
+    for shift in (25, 24, 27):
+        table_p, hist_p, sums_p = z(2 ** 30), z(n, bc), z(n)
+        dev_table15_partitioned(dr, ws, table_p, True, bs, bc, hist_p, sums_p, log2_bucket_keys=shift)      # fused
+        assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d), shift
+    table_p = z(2 ** 30)
+    dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=25)                                        # count only
+    assert torch.equal(table_p, table_d)
+    hist_p, sums_p = z(n, bc), z(n)
+    dev_table15_partitioned(dr, ws, table_d, False, 3, 7, z(n, 7), z(n))                                      # search only, other params
+    dev_table15_partitioned(dr, ws, table_d, False, bs, bc, hist_p, sums_p)
+    assert torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
+    # key shards x block shards accumulate to the whole
+    table_p, hist_p, sums_p = z(2 ** 30), z(n, bc), z(n)
+    nb = pr.n_blocks
+    for klo, khi in ((0, 2 ** 28), (2 ** 28, 2 ** 29), (2 ** 29, 2 ** 30)):
+        for blo, bhi in ((0, nb // 3), (nb // 3, nb)):
+            dev_table15_partitioned(dr, ws, table_p, True, blk_lo=blo, blk_hi=bhi, key_lo=klo, key_hi=khi)
+    assert torch.equal(table_p, table_d)
+    for klo, khi in ((0, 2 ** 28), (2 ** 28, 2 ** 29), (2 ** 29, 2 ** 30)):
+        for blo, bhi in ((0, int(blk[n // 2])), (int(blk[n // 2]), nb)):
+            dev_table15_partitioned(dr, ws, table_p, False, bs, bc, hist_p, sums_p, blk_lo=blo, blk_hi=bhi, key_lo=klo, key_hi=khi)
+    assert torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
+    # workspace too small is an error, not a truncation
+    small = PartitionWorkspace(dr, capacity=1000)
+    with pytest.raises(_lib.LrbError):
+        dev_table15_partitioned(dr, small, z(2 ** 30), True)
+
+
 # ---- full-size properties (BASELINE.json configs) ---------------------------------------------------------
 
 def _full_size_properties(name, subsample=200):
@@ -298,6 +342,15 @@ def _full_size_properties(name, subsample=200):
     sums = torch.zeros(n, dtype=torch.int32, device=DEV)
     dev_search(dr, table, bs, bc, hist, sums)
     assert torch.equal(sums.to(torch.int64), nwin) and torch.equal(hist.sum(dim=1, dtype=torch.int64), nwin)
+    # the L2-resident (partitioned) passes give the same table and histograms at full size
+    ws = PartitionWorkspace(dr)
+    table_p = torch.zeros(2 ** 30, dtype=torch.int32, device=DEV)
+    hist_p = torch.zeros((n, bc), dtype=torch.int32, device=DEV)
+    sums_p = torch.zeros(n, dtype=torch.int32, device=DEV)
+    dev_table15_partitioned(dr, ws, table_p, True, bs, bc, hist_p, sums_p)
+    dev_mirror(table_p)
+    assert torch.equal(table_p, table) and torch.equal(hist_p, hist) and torch.equal(sums_p, sums)
+    del ws, table_p, hist_p, sums_p
     # spot-check reads against the oracle restricted to the sampled reads' own k-mers:
     # composition needs only the read; coverage needs global counts, looked up from the device table
     rng = np.random.default_rng(1)
@@ -308,18 +361,15 @@ def _full_size_properties(name, subsample=200):
     for row, i in enumerate(pick):
         s = layout.unpack(int(i))
         assert np.array_equal(comp_h[row], oracle.composition(s, k)[0].astype(np.uint32)), i
-        # 15-mer keys of this read via the oracle's own rolling code (a private table), then bucket the device counts
-        priv = oracle.Table()
-        priv.count(s)
-        keys = np.flatnonzero(priv.array)
-        mult = priv.array[keys]
-        priv.close()
-        fw = keys  # both strands present; forward windows = half of the total mass, bucket by device count
-        dev_counts = table[torch.from_numpy(fw.astype(np.int64)).to(DEV)].cpu().numpy().view(np.uint32)
+        # coverage needs GLOBAL counts: take this read's window keys from the oracle's rolling code, look their
+        # counts up in the device table (itself checked above by mass / symmetry and, at small sizes, bit for
+        # bit against the oracle) and apply the oracle's bucket rule
+        keys = oracle.window_keys(s)
+        dev_counts = table[torch.from_numpy(keys.astype(np.int64)).to(DEV)].cpu().numpy().view(np.uint32)
         want = np.zeros(bc, dtype=np.uint64)
-        for c, m_ in zip(dev_counts, mult):
-            want[oracle.bucket(int(c), bs, bc)] += int(m_)
-        assert np.array_equal(want, 2 * hist_h[row].astype(np.uint64)), i      # each window seen on both strands
+        for c in dev_counts:
+            want[oracle.bucket(int(c), bs, bc)] += 1
+        assert np.array_equal(want, hist_h[row].astype(np.uint64)), i
     del table, comp, hist
 
 
