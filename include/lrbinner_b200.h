@@ -106,24 +106,33 @@ int lrb_dev_mirror(uint32_t* table, void* stream);
 int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_size, int bins, uint32_t* hist,
                    uint32_t* sums, uint64_t tile_lo, uint64_t tile_hi, uint32_t key_lo, uint32_t key_hi, void* stream);
 
-/* L2-resident variant of count and/or search (csrc/partition.cu): the valid windows of blocks
- * [blk_lo, blk_hi) whose bit-15-clear key lies in [key_lo, key_hi) are partitioned by key >> log2_bucket_keys
- * into at most 64 buckets (key range must be bucket-aligned); then per bucket the keys are applied to the
- * table slice while it is resident in L2.  do_count: table[key] += 1 (as lrb_dev_count; mirror separately).
- * hist != NULL: search (as lrb_dev_search through table[bit-15-clear key]); with do_count the search of a
- * bucket follows its count directly.  blk_read[n_blocks] = read index of every block (lrb_dev_fill_blk_read).
- * Workspace: ws_keys / ws_rids hold ws_capacity u32 each (ws_rids may be NULL when hist is NULL);
- * ws_small >= 192 u64.  Bit-identical to the direct kernels.  Synchronises `stream` once (region sizes). */
+/* L2-resident variant of count and search (csrc/partition.cu).  The valid windows of blocks [blk_lo, blk_hi)
+ * whose bit-15-clear key lies in [key_lo, key_hi) are partitioned ONCE by key >> log2_bucket_keys into at most
+ * 64 buckets (key range bucket-aligned) as (key[, read index]) lists; lrb_dev_partition_apply then walks the
+ * buckets and applies each list to the table slice while that slice is resident in L2:
+ *   mode 1  count : table[key] += 1                    (== lrb_dev_count; mirror separately)
+ *   mode 2  search: hist/sums through table[key]       (== lrb_dev_search on bit-15-clear keys; no mirror needed)
+ *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
+ * A partition can be applied several times (count, exchange tables between GPUs, then search).
+ * blk_read[n_blocks] = read index of every block (lrb_dev_fill_blk_read).  The caller owns the device
+ * buffers named in lrb_partition (keys/rids: `capacity` u32 each, small: >= 192 u64) and fills those fields;
+ * build fills the rest.  Bit-identical to the direct kernels.  build synchronises `stream` once. */
+typedef struct {
+    uint32_t* keys;                /* device, capacity entries */
+    uint32_t* rids;                /* device, capacity entries (NULL if never searching) */
+    unsigned long long* small;     /* device scratch, >= 192 u64 */
+    uint64_t capacity;
+    int n_buckets, shift, has_rids;
+    uint32_t key_lo;
+    unsigned long long count[64];  /* entries per bucket (host copy) */
+    unsigned long long offset[65]; /* first entry of each bucket */
+} lrb_partition;
 int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_read, void* stream);
-int lrb_dev_table15_partitioned(const lrb_reads_view* dev, const uint32_t* blk_read, uint32_t* table, int do_count,
-                                long bin_size, int bins, uint32_t* hist, uint32_t* sums, uint64_t blk_lo,
-                                uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
-                                uint32_t* ws_keys, uint32_t* ws_rids, uint64_t ws_capacity,
-                                unsigned long long* ws_small, void* stream);
-
-/* cudaLimitMaxL2FetchGranularity for the current device (32, 64 or 128 bytes): the table passes are random
- * 4-byte accesses, 32 avoids over-fetching neighbouring sectors from HBM. */
-int lrb_dev_set_l2_fetch_granularity(int bytes);
+int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t* blk_read, int with_rids, uint64_t blk_lo,
+                            uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys, lrb_partition* part,
+                            void* stream);
+int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint32_t* table, long bin_size, int bins, uint32_t* hist,
+                            uint32_t* sums, void* stream);
 
 /* Pack ASCII on the device: bases[] (device, concatenated) -> codes/valid of `dev` (layout prebuilt). */
 int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, const uint64_t* offsets, void* stream);

@@ -28,6 +28,13 @@ class ReadsView(C.Structure):
                 ("tile_read", C.c_void_p), ("tile_blk", C.c_void_p)]
 
 
+class Partition(C.Structure):
+    """lrb_partition: caller-owned device buffers + the bucket layout filled by lrb_dev_partition_build."""
+    _fields_ = [("keys", C.c_void_p), ("rids", C.c_void_p), ("small", C.c_void_p), ("capacity", C.c_uint64),
+                ("n_buckets", C.c_int), ("shift", C.c_int), ("has_rids", C.c_int), ("key_lo", C.c_uint32),
+                ("count", C.c_ulonglong * 64), ("offset", C.c_ulonglong * 65)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_genomes", C.c_uint32), ("sub_thr", C.c_uint32), ("ins_thr", C.c_uint32),
                 ("del_thr", C.c_uint32), ("n_thr", C.c_uint32), ("read_base", C.c_uint64)]
@@ -56,9 +63,8 @@ _SIG = {
     "lrb_dev_search": (C.c_int, [C.POINTER(ReadsView), _P, C.c_long, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
                                  C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_fill_blk_read": (C.c_int, [C.POINTER(ReadsView), _P, _P]),
-    "lrb_dev_table15_partitioned": (C.c_int, [C.POINTER(ReadsView), _P, _P, C.c_int, C.c_long, C.c_int, _P, _P, C.c_uint64,
-                                              C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P, _P, C.c_uint64, _P, _P]),
-    "lrb_dev_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
+    "lrb_dev_partition_build": (C.c_int, [C.POINTER(ReadsView), _P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
+    "lrb_dev_partition_apply": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_int, _P, _P, _P]),
     "lrb_dev_pack_ascii": (C.c_int, [C.POINTER(ReadsView), _P, _P, _P]),
     "lrb_dev_format_composition": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
     "lrb_dev_format_coverage": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),

@@ -40,15 +40,6 @@ void lrb_host_free(void* p, bool pinned) {
     else free(p);
 }
 
-// Random 4-byte table accesses over-fetch when L2 pulls more than one 32 B sector per miss from HBM
-// (ncu: 126 B of DRAM reads per gather at the default setting); 32 asks for single-sector fills.
-extern "C" int lrb_dev_set_l2_fetch_granularity(int bytes) {
-    if (bytes != 32 && bytes != 64 && bytes != 128) return lrb_set_error(LRB_EINVAL, "L2 fetch granularity must be 32, 64 or 128");
-    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
-    if (e != cudaSuccess) return lrb_set_error(LRB_ECUDA, "cudaDeviceSetLimit(L2 fetch granularity) failed: %s", cudaGetErrorString(e));
-    return LRB_OK;
-}
-
 extern "C" void* lrb_pinned_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable) != cudaSuccess) {
@@ -82,6 +73,8 @@ struct lrb_ctx {
     cudaEvent_t ev[8] = {};
     DevBuf codes, valid, read_len, read_blk, tile_read, tile_blk;
     DevBuf table, comp, hist, sums, text;
+    DevBuf part_keys, part_rids, part_small, blk_read;  // L2-resident (partitioned) table passes
+    lrb_partition part = {};
     bool table_ready = false;  // holds a complete (mirrored) table
     lrb_reads_view dview = {};
     float ms[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -119,7 +112,7 @@ extern "C" void lrb_ctx_destroy(lrb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->codes, &c->valid, &c->read_len, &c->read_blk, &c->tile_read, &c->tile_blk, &c->table, &c->comp,
-                      &c->hist, &c->sums, &c->text})
+                      &c->hist, &c->sums, &c->text, &c->part_keys, &c->part_rids, &c->part_small, &c->blk_read})
         b->release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -176,6 +169,34 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         if ((rc = c->sums.reserve(std::max<size_t>(16, sizeof(uint32_t) * n)))) return rc;
     }
     if ((do_count || do_search) && (rc = c->table.reserve(sizeof(uint32_t) * (size_t)kTableEntries))) return rc;
+    // table passes: key-partitioned + L2-resident (csrc/partition.cu) unless LRB_TABLE_PATH=direct or its
+    // workspace (8 B per base) does not fit; the direct kernels (one random HBM access per window) remain as
+    // the small-memory GPU path.  Both are bit-identical.
+    bool use_part = (do_count || do_search) && r->n_blocks > 0;
+    {
+        const char* e = getenv("LRB_TABLE_PATH");
+        if (e && !strcmp(e, "direct")) use_part = false;
+    }
+    int bucket_shift = 24;
+    {
+        const char* e = getenv("LRB_BUCKET_LOG2");
+        if (e && atoi(e) >= 24 && atoi(e) <= 30) bucket_shift = atoi(e);
+    }
+    if (use_part) {
+        const size_t cap = std::max<uint64_t>(r->total_bases, 1);
+        if (c->part_keys.reserve(sizeof(uint32_t) * cap) || (do_search && c->part_rids.reserve(sizeof(uint32_t) * cap)) ||
+            c->part_small.reserve(sizeof(unsigned long long) * 256) || c->blk_read.reserve(sizeof(uint32_t) * (r->n_blocks + 1))) {
+            cudaGetLastError();
+            c->part_keys.release();
+            c->part_rids.release();
+            use_part = false;
+        } else {
+            c->part.keys = (uint32_t*)c->part_keys.p;
+            c->part.rids = do_search ? (uint32_t*)c->part_rids.p : nullptr;
+            c->part.small = (unsigned long long*)c->part_small.p;
+            c->part.capacity = cap;
+        }
+    }
 
     CTX_CUDA(cudaEventRecord(c->ev[0], st));
     if ((rc = upload_reads(c, r))) return rc;
@@ -185,9 +206,24 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         if ((rc = lrb_dev_composition(&c->dview, k, (uint32_t*)c->comp.p, 0, r->n_tiles, st))) return rc;
     }
     CTX_CUDA(cudaEventRecord(c->ev[2], st));
+    if (do_search && n) {
+        CTX_CUDA(cudaMemsetAsync(c->hist.p, 0, sizeof(uint32_t) * n * (size_t)bins, st));
+        CTX_CUDA(cudaMemsetAsync(c->sums.p, 0, sizeof(uint32_t) * n, st));
+    }
     if (do_count) {
         c->table_ready = false;
         CTX_CUDA(cudaMemsetAsync(c->table.p, 0, sizeof(uint32_t) * (size_t)kTableEntries, st));
+    }
+    if (use_part) {
+        if (do_search && (rc = lrb_dev_fill_blk_read(&c->dview, (uint32_t*)c->blk_read.p, st))) return rc;
+        if ((rc = lrb_dev_partition_build(&c->dview, (const uint32_t*)c->blk_read.p, do_search ? 1 : 0, 0, r->n_blocks, 0, kTableEntries,
+                                          bucket_shift, &c->part, st)))
+            return rc;
+        const int mode = (do_count ? 1 : 0) | (do_search && n ? 2 : 0);
+        if (mode && (rc = lrb_dev_partition_apply(&c->part, mode, (uint32_t*)c->table.p, bin_size, bins, (uint32_t*)c->hist.p,
+                                                  (uint32_t*)c->sums.p, st)))
+            return rc;
+    } else if (do_count) {
         if ((rc = lrb_dev_count(&c->dview, (uint32_t*)c->table.p, 0, r->n_blocks, 0, kTableEntries, st))) return rc;
     }
     CTX_CUDA(cudaEventRecord(c->ev[3], st));
@@ -196,9 +232,7 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         c->table_ready = true;
     }
     CTX_CUDA(cudaEventRecord(c->ev[4], st));
-    if (do_search && n) {
-        CTX_CUDA(cudaMemsetAsync(c->hist.p, 0, sizeof(uint32_t) * n * (size_t)bins, st));
-        CTX_CUDA(cudaMemsetAsync(c->sums.p, 0, sizeof(uint32_t) * n, st));
+    if (!use_part && do_search && n) {
         if ((rc = lrb_dev_search(&c->dview, (const uint32_t*)c->table.p, bin_size, bins, (uint32_t*)c->hist.p,
                                  (uint32_t*)c->sums.p, 0, r->n_tiles, 0, kTableEntries, st)))
             return rc;

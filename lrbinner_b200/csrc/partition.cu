@@ -235,31 +235,33 @@ extern "C" int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_re
     return LRB_OK;
 }
 
-extern "C" int lrb_dev_table15_partitioned(const lrb_reads_view* dev, const uint32_t* blk_read, uint32_t* table, int do_count,
-                                           long bin_size, int bins, uint32_t* hist, uint32_t* sums, uint64_t blk_lo,
-                                           uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
-                                           uint32_t* ws_keys, uint32_t* ws_rids, uint64_t ws_capacity,
-                                           unsigned long long* ws_small, void* stream) {
-    if (!dev || !table || !ws_keys || !ws_small) return lrb_set_error(LRB_EINVAL, "lrb_dev_table15_partitioned: null argument");
-    const bool do_search = hist != nullptr;
-    if (!do_count && !do_search) return LRB_OK;
-    if (do_search && (!sums || !ws_rids || !blk_read)) return lrb_set_error(LRB_EINVAL, "lrb_dev_table15_partitioned: search needs sums, ws_rids and blk_read");
-    if (do_search && bin_size <= 0) return lrb_set_error(LRB_EINVAL, "bin_size must be >= 1 (the reference divides by it)");
-    if (do_search && (bins <= 0 || bins > LRB_MAX_BINS)) return lrb_set_error(LRB_EINVAL, "bins must be in [1, %d]", LRB_MAX_BINS);
+// ---- host side: build the partition once, then count and/or search bucket by bucket ---------------------------
+extern "C" int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t* blk_read, int with_rids, uint64_t blk_lo,
+                                       uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
+                                       lrb_partition* part, void* stream) {
+    if (!dev || !part || !part->keys || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_build: null argument");
+    if (with_rids && (!part->rids || !blk_read)) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_build: read ids need part->rids and blk_read");
     if (key_hi > kTableEntries) key_hi = kTableEntries;
     if (blk_hi > dev->n_blocks) blk_hi = dev->n_blocks;
-    if (blk_lo >= blk_hi || key_lo >= key_hi) return LRB_OK;
     const int shift = log2_bucket_keys;
     if (shift < 20 || shift > 30) return lrb_set_error(LRB_EINVAL, "log2_bucket_keys must be in [20, 30]");
     const uint32_t bsz = 1u << shift;
-    if ((key_lo & (bsz - 1)) || (key_hi & (bsz - 1))) return lrb_set_error(LRB_EINVAL, "key range must be aligned to the bucket size 2^%d", shift);
+    if (key_lo >= key_hi || (key_lo & (bsz - 1)) || (key_hi & (bsz - 1)))
+        return lrb_set_error(LRB_EINVAL, "key range must be non-empty and aligned to the bucket size 2^%d", shift);
     const int nb = (int)((key_hi - key_lo) >> shift);
     if (nb < 1 || nb > kMaxBuckets) return lrb_set_error(LRB_EINVAL, "key range spans %d buckets (max %d): raise log2_bucket_keys", nb, kMaxBuckets);
+    part->n_buckets = nb;
+    part->shift = shift;
+    part->key_lo = key_lo;
+    part->has_rids = with_rids ? 1 : 0;
+    for (int b = 0; b <= kMaxBuckets; ++b) part->offset[b] = 0;
+    for (int b = 0; b < kMaxBuckets; ++b) part->count[b] = 0;
+    if (blk_lo >= blk_hi) return LRB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long* d_counts = ws_small;                 // [64]
-    unsigned long long* d_offsets = ws_small + kMaxBuckets;  // [64]
-    unsigned long long* d_cursor = ws_small + 2 * kMaxBuckets;  // [64]
-    LRB_CUDA(cudaMemsetAsync(ws_small, 0, sizeof(unsigned long long) * 3 * kMaxBuckets, st));
+    unsigned long long* d_counts = part->small;                    // [64]
+    unsigned long long* d_offsets = part->small + kMaxBuckets;     // [64]
+    unsigned long long* d_cursor = part->small + 2 * kMaxBuckets;  // [64]
+    LRB_CUDA(cudaMemsetAsync(part->small, 0, sizeof(unsigned long long) * 3 * kMaxBuckets, st));
     const uint64_t nblk = blk_hi - blk_lo;
     const int nsm = sms();
     {
@@ -268,39 +270,51 @@ extern "C" int lrb_dev_table15_partitioned(const lrb_reads_view* dev, const uint
         k_bucket_hist<<<grid, 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, key_lo, key_hi, shift, d_counts);
         LRB_CUDA(cudaGetLastError());
     }
-    unsigned long long h_counts[kMaxBuckets], h_offsets[kMaxBuckets + 1];
-    LRB_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof h_counts, cudaMemcpyDeviceToHost, st));
+    LRB_CUDA(cudaMemcpyAsync(part->count, d_counts, sizeof(unsigned long long) * kMaxBuckets, cudaMemcpyDeviceToHost, st));
     LRB_CUDA(cudaStreamSynchronize(st));  // the one host round trip: region sizes
-    h_offsets[0] = 0;
-    for (int b = 0; b < kMaxBuckets; ++b) h_offsets[b + 1] = h_offsets[b] + (b < nb ? h_counts[b] : 0ull);
-    const unsigned long long total = h_offsets[nb];
-    if (total > ws_capacity)
-        return lrb_set_error(LRB_ENOMEM, "partition workspace too small: %llu entries needed, %llu available", total, (unsigned long long)ws_capacity);
-    LRB_CUDA(cudaMemcpyAsync(d_offsets, h_offsets, sizeof(unsigned long long) * kMaxBuckets, cudaMemcpyHostToDevice, st));
-    {
-        const uint64_t n_chunks = (nblk + kPartThreads - 1) / kPartThreads;
-        const unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)nsm * 16);
-        if (do_search) {
-            const size_t smem = sizeof(uint32_t) * 2 * kChunkSlots;
-            LRB_CUDA(cudaFuncSetAttribute(k_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_partition<true><<<grid, kPartThreads, smem, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, key_lo, key_hi, shift,
-                                                                  nb, d_offsets, d_cursor, ws_keys, ws_rids);
-        } else {
-            const size_t smem = sizeof(uint32_t) * kChunkSlots;
-            k_partition<false><<<grid, kPartThreads, smem, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, key_lo, key_hi, shift,
-                                                                   nb, d_offsets, d_cursor, ws_keys, ws_rids);
-        }
-        LRB_CUDA(cudaGetLastError());
+    for (int b = 0; b < kMaxBuckets; ++b) part->offset[b + 1] = part->offset[b] + (b < nb ? part->count[b] : 0ull);
+    const unsigned long long total = part->offset[nb];
+    if (total > part->capacity)
+        return lrb_set_error(LRB_ENOMEM, "partition workspace too small: %llu entries needed, %llu available", total, (unsigned long long)part->capacity);
+    LRB_CUDA(cudaMemcpyAsync(d_offsets, part->offset, sizeof(unsigned long long) * kMaxBuckets, cudaMemcpyHostToDevice, st));
+    const uint64_t n_chunks = (nblk + kPartThreads - 1) / kPartThreads;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)nsm * 16);
+    if (with_rids) {
+        const size_t smem = sizeof(uint32_t) * 2 * kChunkSlots;
+        LRB_CUDA(cudaFuncSetAttribute(k_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_partition<true><<<grid, kPartThreads, smem, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, key_lo, key_hi, shift, nb,
+                                                              d_offsets, d_cursor, part->keys, part->rids);
+    } else {
+        const size_t smem = sizeof(uint32_t) * kChunkSlots;
+        k_partition<false><<<grid, kPartThreads, smem, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, key_lo, key_hi, shift, nb,
+                                                               d_offsets, d_cursor, part->keys, part->rids);
     }
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+// mode bit 0: count (table[key] += 1), bit 1: search (hist/sums through table[key]); both = per bucket count then search
+extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint32_t* table, long bin_size, int bins,
+                                       uint32_t* hist, uint32_t* sums, void* stream) {
+    if (!part || !table) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: null argument");
+    const bool do_count = mode & 1, do_search = mode & 2;
+    if (do_search) {
+        if (!hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: search needs hist and sums");
+        if (!part->has_rids) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: partition was built without read ids");
+        if (bin_size <= 0) return lrb_set_error(LRB_EINVAL, "bin_size must be >= 1 (the reference divides by it)");
+        if (bins <= 0 || bins > LRB_MAX_BINS) return lrb_set_error(LRB_EINVAL, "bins must be in [1, %d]", LRB_MAX_BINS);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
     const uint32_t S32 = bin_size > 0xFFFFFFFFl ? 0xFFFFFFFFu : (uint32_t)(bin_size > 0 ? bin_size : 1);
     const uint64_t magic = coverage_magic(S32);
-    for (int b = 0; b < nb; ++b) {
-        const uint64_t n = h_counts[b];
+    const int nsm = sms();
+    for (int b = 0; b < part->n_buckets; ++b) {
+        const uint64_t n = part->count[b];
         if (!n) continue;
-        const uint32_t* kb = ws_keys + h_offsets[b];
+        const uint32_t* kb = part->keys + part->offset[b];
         const unsigned grid = (unsigned)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)nsm * 8);
         if (do_count) k_count_keys<<<grid, 256, 0, st>>>(kb, n, table);
-        if (do_search) k_search_keys<<<grid, 256, 0, st>>>(kb, ws_rids + h_offsets[b], n, table, S32, magic, (uint32_t)bins, hist, sums);
+        if (do_search) k_search_keys<<<grid, 256, 0, st>>>(kb, part->rids + part->offset[b], n, table, S32, magic, (uint32_t)bins, hist, sums);
     }
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;

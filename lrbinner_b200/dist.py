@@ -41,16 +41,23 @@ def key_range(world, rank, entries=TABLE_ENTRIES):
 
 
 class CudaEngine:
-    """Per-GPU work through the C ABI kernels on torch CUDA tensors (the product path)."""
+    """Per-GPU work through the C ABI kernels on torch CUDA tensors (the product path).
 
-    def __init__(self, device_reads):
+    Table passes go through the key-partitioned, L2-resident kernels (csrc/partition.cu): count() builds the
+    partition of the requested (reads x keys) rectangle and applies it; search() re-uses that partition when it
+    covers the same rectangle (plans A and X: count -> exchange -> search on the same lists), else builds its own."""
+
+    def __init__(self, device_reads, workspace_entries=None, log2_bucket_keys=24):
         import torch
         from . import profile
         self.torch, self.p, self.dr = torch, profile, device_reads
         self.n_reads = device_reads.n_reads
         self.device = device_reads.device
         self.table_entries = TABLE_ENTRIES          # 4^15 (count-15mers.cpp:99)
+        self.shift = log2_bucket_keys
         self._rb = None
+        self.ws = profile.PartitionWorkspace(device_reads, capacity=workspace_entries)
+        self._rect = None
 
     def zeros(self, shape):
         return self.torch.zeros(shape, dtype=self.torch.int32, device=self.device)
@@ -60,20 +67,31 @@ class CudaEngine:
             self._rb = self.dr.read_blk.cpu().numpy().view(np.uint32)
         return int(self._rb[lo]), int(self._rb[hi])
 
+    def _partition(self, read_lo, read_hi, key_lo, key_hi):
+        rect = (read_lo, read_hi, key_lo, key_hi)
+        if self._rect != rect:
+            blo, bhi = self._blocks(read_lo, read_hi)
+            shift = self.shift
+            while (key_hi - key_lo) >> shift > 64:
+                shift += 1
+            self.ws.build(True, blo, bhi, key_lo, key_hi, shift, grow=True)
+            self._rect = rect
+
     def composition(self, k, comp, read_lo, read_hi):
         tlo, thi = self.dr.tile_range_for_reads(read_lo, read_hi)
         self.p.dev_composition(self.dr, k, comp, tlo, thi)
 
     def count(self, table, key_lo, key_hi, read_lo, read_hi):
-        blo, bhi = self._blocks(read_lo, read_hi)
-        self.p.dev_count(self.dr, table, blo, bhi, key_lo, key_hi)
+        self._rect = None                            # new step: the reads may have been re-uploaded
+        self._partition(read_lo, read_hi, key_lo, key_hi)
+        self.ws.apply(table, count=True)
 
     def mirror(self, table):
         self.p.dev_mirror(table)
 
     def search(self, table, bin_size, bins, hist, sums, read_lo, read_hi, key_lo, key_hi):
-        tlo, thi = self.dr.tile_range_for_reads(read_lo, read_hi)
-        self.p.dev_search(self.dr, table, bin_size, bins, hist, sums, tlo, thi, key_lo, key_hi)
+        self._partition(read_lo, read_hi, key_lo, key_hi)
+        self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums)
 
 
 def _reduce_scatter(dist, out, inp, group):
@@ -180,7 +198,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     spec = SynthSpec(n_shard * world, lengths=cfg["lengths"], errors=cfg["errors"], seed=cfg["seed"])
     dr, layout = spec.device_reads(dev)
     n, L = spec.n_reads, spec.total_bases
-    eng = CudaEngine(dr)
+    eng = CudaEngine(dr, workspace_entries=int(L / world * 1.25) + (1 << 20))
     table = torch.zeros(TABLE_ENTRIES, dtype=torch.int32, device=dev)
 
     def timed(plan, steps):
@@ -214,7 +232,9 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     sampler.start()
     ms_step, res, phases = timed(best, args.steps)
     clocks = sampler.stop()
-    launches = {"keyshard_rs": 3, "keyshard_ag": 4, "readshard_ar": 4}[best] * args.steps
+    nbk = eng.ws.part.n_buckets
+    # composition + bucket_hist + partition + per-bucket count and search kernels (+ mirror; plan B partitions twice)
+    launches = {"keyshard_rs": 3 + 2 * nbk, "keyshard_ag": 6 + 2 * nbk, "readshard_ar": 4 + 2 * nbk}[best] * args.steps
 
     # e2e: every step also moves this rank's inputs host->device and its result rows device->host
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

@@ -246,26 +246,54 @@ def dev_search(dr, table, bin_size, bins, hist, sums, tile_lo=0, tile_hi=None, k
 
 
 class PartitionWorkspace:
-    """Scratch for the L2-resident table passes: (key, read) lists of up to `capacity` windows + the per-block read index."""
+    """Scratch of the L2-resident table passes: (key, read) lists for up to `capacity` windows, the per-block
+    read index, and the lrb_partition descriptor the C ABI fills."""
 
     def __init__(self, dr, capacity=None, with_rids=True):
         torch = dr.torch
+        self.dr = dr
         self.capacity = int(capacity if capacity is not None else max(dr.total_bases, 1))
         self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
         self.rids = torch.empty(self.capacity, dtype=torch.int32, device=dr.device) if with_rids else None
         self.small = torch.zeros(256, dtype=torch.int64, device=dr.device)
         self.blk_read = torch.empty(max(dr.n_blocks, 1), dtype=torch.int32, device=dr.device)
         check(lib.lrb_dev_fill_blk_read(C.byref(dr.view), C.c_void_p(self.blk_read.data_ptr()), _stream()))
+        self.part = _lib.Partition(keys=self.keys.data_ptr(), rids=self.rids.data_ptr() if with_rids else None,
+                                   small=self.small.data_ptr(), capacity=self.capacity)
+
+    def build(self, with_rids=True, blk_lo=0, blk_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, grow=False):
+        args = (C.byref(self.dr.view), C.c_void_p(self.blk_read.data_ptr()), 1 if with_rids else 0, blk_lo,
+                self.dr.n_blocks if blk_hi is None else blk_hi, key_lo, min(key_hi, _lib.TABLE_ENTRIES), log2_bucket_keys,
+                C.byref(self.part), _stream())
+        rc = lib.lrb_dev_partition_build(*args)
+        if rc == _lib.LRB_ENOMEM and grow:      # the exact pre-pass told us the size: grow the lists once and retry
+            torch = self.dr.torch
+            need = int(self.part.offset[self.part.n_buckets])
+            self.keys = self.rids = None
+            torch.cuda.empty_cache()
+            self.capacity = need + need // 64 + 1024
+            self.keys = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
+            self.rids = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
+            self.part.keys, self.part.rids, self.part.capacity = self.keys.data_ptr(), self.rids.data_ptr(), self.capacity
+            rc = lib.lrb_dev_partition_build(*args)
+        check(rc)
+
+    def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None):
+        mode = (1 if count else 0) | (2 if search else 0)
+        check(lib.lrb_dev_partition_apply(C.byref(self.part), mode, C.c_void_p(table.data_ptr()), bin_size, bins,
+                                          C.c_void_p(hist.data_ptr()) if hist is not None else None,
+                                          C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream()))
+
+    def total_entries(self):
+        return int(self.part.offset[self.part.n_buckets])
 
 
 def dev_table15_partitioned(dr, ws, table, do_count=True, bin_size=1, bins=1, hist=None, sums=None, blk_lo=0, blk_hi=None,
-                            key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=25):
-    check(lib.lrb_dev_table15_partitioned(
-        C.byref(dr.view), C.c_void_p(ws.blk_read.data_ptr()), C.c_void_p(table.data_ptr()), 1 if do_count else 0, bin_size, bins,
-        C.c_void_p(hist.data_ptr()) if hist is not None else None, C.c_void_p(sums.data_ptr()) if sums is not None else None,
-        blk_lo, dr.n_blocks if blk_hi is None else blk_hi, key_lo, min(key_hi, _lib.TABLE_ENTRIES), log2_bucket_keys,
-        C.c_void_p(ws.keys.data_ptr()), C.c_void_p(ws.rids.data_ptr()) if ws.rids is not None else None, ws.capacity,
-        C.c_void_p(ws.small.data_ptr()), _stream()))
+                            key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24):
+    """One-shot: partition the windows of [blk_lo, blk_hi) x [key_lo, key_hi), then count and/or search per bucket."""
+    search = hist is not None
+    ws.build(search, blk_lo, blk_hi, key_lo, key_hi, log2_bucket_keys)
+    ws.apply(table, do_count, search, bin_size, bins, hist, sums)
 
 
 def dev_format_composition(counts, read_len, n_reads, k, text):

@@ -8,10 +8,6 @@ from lrbinner_b200.synth import CONFIGS, SynthSpec
 
 dev = torch.device("cuda:0")
 torch.cuda.init(); torch.zeros(1, device=dev)
-if os.environ.get("LRB_L2_FETCH"):
-    from lrbinner_b200._lib import lib, check
-    check(lib.lrb_dev_set_l2_fetch_granularity(int(os.environ["LRB_L2_FETCH"])))
-    print(json.dumps({"l2_fetch_granularity": int(os.environ["LRB_L2_FETCH"])}), flush=True)
 cfg = CONFIGS["cfg2_1M_5kb_ont_k4"]
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
 spec = SynthSpec(n_reads, lengths=cfg["lengths"], errors=cfg["errors"], seed=cfg["seed"])

@@ -7,10 +7,6 @@ from lrbinner_b200.synth import CONFIGS, SynthSpec
 
 dev = torch.device("cuda:0")
 torch.cuda.init(); torch.zeros(1, device=dev)
-if os.environ.get("LRB_L2_FETCH"):
-    from lrbinner_b200._lib import lib, check
-    check(lib.lrb_dev_set_l2_fetch_granularity(int(os.environ["LRB_L2_FETCH"])))
-    print(json.dumps({"l2_fetch_granularity": int(os.environ["LRB_L2_FETCH"])}), flush=True)
 cfg_name = sys.argv[2] if len(sys.argv) > 2 else "cfg2_1M_5kb_ont_k4"
 cfg = CONFIGS[cfg_name]
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else cfg["n_reads"]
