@@ -106,31 +106,41 @@ int lrb_dev_mirror(uint32_t* table, void* stream);
 int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_size, int bins, uint32_t* hist,
                    uint32_t* sums, uint64_t tile_lo, uint64_t tile_hi, uint32_t key_lo, uint32_t key_hi, void* stream);
 
-/* L2-resident variant of count and search (csrc/partition.cu).  The valid windows of blocks [blk_lo, blk_hi)
- * whose bit-15-clear key lies in [key_lo, key_hi) are partitioned ONCE by key >> log2_bucket_keys into at most
- * 64 buckets (key range bucket-aligned) as (key[, read index]) lists; lrb_dev_partition_apply then walks the
- * buckets and applies each list to the table slice while that slice is resident in L2:
+/* L2-resident variant of count and search (csrc/partition.cu).  The valid windows whose bit-15-clear key lies
+ * in [key_lo, key_hi) are partitioned ONCE by key >> log2_bucket_keys into at most 64 buckets (key range
+ * bucket-aligned) as (key[, read index]) lists; lrb_dev_partition_apply then walks the buckets and applies each
+ * list to the table slice while that slice is resident in L2:
  *   mode 1  count : table[key] += 1                    (== lrb_dev_count; mirror separately)
  *   mode 2  search: hist/sums through table[key]       (== lrb_dev_search on bit-15-clear keys; no mirror needed)
  *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
- * A partition can be applied several times (count, exchange tables between GPUs, then search).
- * blk_read[n_blocks] = read index of every block (lrb_dev_fill_blk_read).  The caller owns the device
- * buffers named in lrb_partition (keys/rids: `capacity` u32 each, small: >= 192 u64) and fills those fields;
- * build fills the rest.  Bit-identical to the direct kernels.  build synchronises `stream` once. */
+ * begin() resets the lists; add() appends the windows of blocks [blk_lo, blk_hi) as one chunk (up to 64 chunks,
+ * e.g. one per host-to-device copy so partitioning overlaps the transfer); build() = begin + one add.  A
+ * partition can be applied several times (count, exchange tables between GPUs, then search).  Everything is
+ * asynchronous on `stream`; sizes are computed on the device.  If the lists would exceed `capacity` the chunk is
+ * dropped and a device flag is raised: lrb_dev_partition_check (synchronises) returns LRB_ENOMEM and the number
+ * of entries needed.  capacity >= total number of slots can never overflow.
+ * blk_read[n_blocks] = read index of every block (lrb_dev_fill_blk_read).  The caller owns the device buffers and
+ * fills keys/rids/small/capacity; the library fills the rest.  Bit-identical to the direct kernels. */
+#define LRB_PART_MAX_BUCKETS 64
+#define LRB_PART_MAX_CHUNKS 64
+#define LRB_PART_SMALL_U64 16384
 typedef struct {
     uint32_t* keys;                /* device, capacity entries */
     uint32_t* rids;                /* device, capacity entries (NULL if never searching) */
-    unsigned long long* small;     /* device scratch, >= 192 u64 */
+    unsigned long long* small;     /* device scratch, LRB_PART_SMALL_U64 u64 */
     uint64_t capacity;
-    int n_buckets, shift, has_rids;
-    uint32_t key_lo;
-    unsigned long long count[64];  /* entries per bucket (host copy) */
-    unsigned long long offset[65]; /* first entry of each bucket */
+    int n_buckets, shift, has_rids, n_chunks;
+    uint32_t key_lo, key_hi;
 } lrb_partition;
 int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_read, void* stream);
+int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
+                            void* stream);
+int lrb_dev_partition_add(const lrb_reads_view* dev, const uint32_t* blk_read, uint64_t blk_lo, uint64_t blk_hi,
+                          lrb_partition* part, void* stream);
 int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t* blk_read, int with_rids, uint64_t blk_lo,
                             uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys, lrb_partition* part,
                             void* stream);
+int lrb_dev_partition_check(const lrb_partition* part, uint64_t* needed, void* stream);
 int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint32_t* table, long bin_size, int bins, uint32_t* hist,
                             uint32_t* sums, void* stream);
 
@@ -169,14 +179,17 @@ int lrb_ctx_create(int device, lrb_ctx** out);
 void lrb_ctx_destroy(lrb_ctx* ctx);
 
 /* Whole profile stage for one read set held in (pinned) HOST memory:
- *   H2D(packed reads) -> composition -> 15-mer count -> mirror -> search -> D2H(results).
+ *   H2D(packed reads, chunked) || composition + key partition per chunk -> count + search per bucket (L2-resident)
+ *   -> mirror -> D2H(results; composition rows return while the table passes run).
  * comp_counts[N*P] (P from k), cov_hist[N*bins], cov_sums[N] are HOST buffers (may be NULL to skip the
  * corresponding phase).  If table_host != NULL the 4 GiB table is copied back as well.
  * If use_loaded_table != 0 the count phase is skipped and the table already in the context is searched. */
 int lrb_profile_host(lrb_ctx* ctx, const lrb_reads* reads, int k, long bin_size, int bins, uint32_t* comp_counts,
                      uint32_t* cov_hist, uint32_t* cov_sums, uint32_t* table_host, int use_loaded_table);
-/* Per-phase device milliseconds of the last lrb_profile_host call:
- * [0] h2d [1] composition [2] memset+count [3] mirror [4] search [5] d2h [6] total */
+/* Device milliseconds (CUDA events) of the last lrb_profile_host call.  The call is a 3-stream pipeline, so the
+ * phases overlap: [0] H2D of the packed reads (copy stream) [1] composition + partition until the last chunk is
+ * processed (runs beside [0]) [2] table passes (count + search per bucket) [3] mirror [4] direct search (only
+ * on the LRB_TABLE_PATH=direct path) [5] result D2H tail [6] the whole call */
 int lrb_ctx_last_timings(const lrb_ctx* ctx, float* ms7);
 /* page-locked host memory for result buffers of lrb_profile_host (NULL + lrb_last_error on failure) */
 void* lrb_pinned_alloc(size_t bytes);

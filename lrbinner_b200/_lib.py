@@ -29,10 +29,13 @@ class ReadsView(C.Structure):
 
 
 class Partition(C.Structure):
-    """lrb_partition: caller-owned device buffers + the bucket layout filled by lrb_dev_partition_build."""
+    """lrb_partition: caller-owned device buffers + the bucket layout filled by lrb_dev_partition_begin/add."""
     _fields_ = [("keys", C.c_void_p), ("rids", C.c_void_p), ("small", C.c_void_p), ("capacity", C.c_uint64),
-                ("n_buckets", C.c_int), ("shift", C.c_int), ("has_rids", C.c_int), ("key_lo", C.c_uint32),
-                ("count", C.c_ulonglong * 64), ("offset", C.c_ulonglong * 65)]
+                ("n_buckets", C.c_int), ("shift", C.c_int), ("has_rids", C.c_int), ("n_chunks", C.c_int),
+                ("key_lo", C.c_uint32), ("key_hi", C.c_uint32)]
+
+
+PART_SMALL_U64 = 16384
 
 
 class SynthParams(C.Structure):
@@ -63,6 +66,9 @@ _SIG = {
     "lrb_dev_search": (C.c_int, [C.POINTER(ReadsView), _P, C.c_long, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
                                  C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_fill_blk_read": (C.c_int, [C.POINTER(ReadsView), _P, _P]),
+    "lrb_dev_partition_begin": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, C.c_int, _P]),
+    "lrb_dev_partition_add": (C.c_int, [C.POINTER(ReadsView), _P, C.c_uint64, C.c_uint64, _P, _P]),
+    "lrb_dev_partition_check": (C.c_int, [_P, _P, _P]),
     "lrb_dev_partition_build": (C.c_int, [C.POINTER(ReadsView), _P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
     "lrb_dev_partition_apply": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_int, _P, _P, _P]),
     "lrb_dev_pack_ascii": (C.c_int, [C.POINTER(ReadsView), _P, _P, _P]),

@@ -69,8 +69,9 @@ struct DevBuf {
 
 struct lrb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t sync_ev[LRB_PART_MAX_CHUNKS + 2] = {};  // [0] index arrays, [1..] H2D chunks, [last] composition D2H
     DevBuf codes, valid, read_len, read_blk, tile_read, tile_blk;
     DevBuf table, comp, hist, sums, text;
     DevBuf part_keys, part_rids, part_small, blk_read;  // L2-resident (partitioned) table passes
@@ -102,7 +103,13 @@ extern "C" int lrb_ctx_create(int device, lrb_ctx** out) {
         delete c;
         return lrb_set_error(LRB_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    if (cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+        lrb_ctx_destroy(c);
+        return lrb_set_error(LRB_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     for (auto& ev : c->ev) cudaEventCreate(&ev);
+    for (auto& ev : c->sync_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = c;
     return LRB_OK;
 }
@@ -115,6 +122,9 @@ extern "C" void lrb_ctx_destroy(lrb_ctx* c) {
                       &c->hist, &c->sums, &c->text, &c->part_keys, &c->part_rids, &c->part_small, &c->blk_read})
         b->release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->sync_ev) if (ev) cudaEventDestroy(ev);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -147,6 +157,10 @@ static int upload_reads(lrb_ctx* c, const lrb_reads* r) {
     return LRB_OK;
 }
 
+// Seam-to-seam pipeline.  Three streams: copy_in streams the packed reads in chunks (cut at read boundaries),
+// `stream` runs composition + partition of chunk i as soon as it has landed (so the kernels that only need the
+// reads overlap the PCIe transfer), then the table passes; copy_out returns the composition rows while the
+// table passes run.  Phase timings (lrb_ctx_last_timings) therefore overlap; [6] is the wall of the whole call.
 extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_size, int bins, uint32_t* comp_counts,
                                 uint32_t* cov_hist, uint32_t* cov_sums, uint32_t* table_host, int use_loaded_table) {
     if (!c || !r) return lrb_set_error(LRB_EINVAL, "lrb_profile_host: null argument");
@@ -159,10 +173,16 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
     if (use_loaded_table && !c->table_ready) return lrb_set_error(LRB_EINVAL, "no table loaded in this context");
     const bool do_count = !use_loaded_table && (do_search || table_host);
     CTX_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
-    const uint64_t n = r->n_reads;
+    cudaStream_t st = c->stream, sin = c->copy_in, sout = c->copy_out;
+    const uint64_t n = r->n_reads, nb = r->n_blocks, nt = r->n_tiles;
     int rc;
-    // allocate before timing starts
+    // ---- allocate before timing starts ------------------------------------------------------------------
+    if ((rc = c->codes.reserve(sizeof(uint32_t) * (2 * nb + 2)))) return rc;
+    if ((rc = c->valid.reserve(sizeof(uint32_t) * (nb + 1)))) return rc;
+    if ((rc = c->read_len.reserve(sizeof(uint32_t) * (n + 1)))) return rc;
+    if ((rc = c->read_blk.reserve(sizeof(uint32_t) * (n + 1)))) return rc;
+    if ((rc = c->tile_read.reserve(sizeof(uint32_t) * (nt + 1)))) return rc;
+    if ((rc = c->tile_blk.reserve(sizeof(uint32_t) * (nt + 1)))) return rc;
     if (comp_counts && (rc = c->comp.reserve(std::max<size_t>(16, sizeof(uint32_t) * n * P)))) return rc;
     if (do_search) {
         if ((rc = c->hist.reserve(std::max<size_t>(16, sizeof(uint32_t) * n * (size_t)bins)))) return rc;
@@ -170,9 +190,9 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
     }
     if ((do_count || do_search) && (rc = c->table.reserve(sizeof(uint32_t) * (size_t)kTableEntries))) return rc;
     // table passes: key-partitioned + L2-resident (csrc/partition.cu) unless LRB_TABLE_PATH=direct or its
-    // workspace (8 B per base) does not fit; the direct kernels (one random HBM access per window) remain as
+    // workspace (8 B per slot) does not fit; the direct kernels (one random HBM access per window) remain as
     // the small-memory GPU path.  Both are bit-identical.
-    bool use_part = (do_count || do_search) && r->n_blocks > 0;
+    bool use_part = (do_count || do_search) && nb > 0;
     {
         const char* e = getenv("LRB_TABLE_PATH");
         if (e && !strcmp(e, "direct")) use_part = false;
@@ -183,9 +203,9 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         if (e && atoi(e) >= 24 && atoi(e) <= 30) bucket_shift = atoi(e);
     }
     if (use_part) {
-        const size_t cap = std::max<uint64_t>(r->total_bases, 1);
+        const size_t cap = std::max<uint64_t>(nb * 32, 1);  // >= number of slots: the lists can never overflow
         if (c->part_keys.reserve(sizeof(uint32_t) * cap) || (do_search && c->part_rids.reserve(sizeof(uint32_t) * cap)) ||
-            c->part_small.reserve(sizeof(unsigned long long) * 256) || c->blk_read.reserve(sizeof(uint32_t) * (r->n_blocks + 1))) {
+            c->part_small.reserve(sizeof(unsigned long long) * LRB_PART_SMALL_U64) || c->blk_read.reserve(sizeof(uint32_t) * (nb + 1))) {
             cudaGetLastError();
             c->part_keys.release();
             c->part_rids.release();
@@ -197,15 +217,55 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             c->part.capacity = cap;
         }
     }
+    lrb_reads_view& v = c->dview;
+    v.n_reads = n; v.n_blocks = nb; v.n_tiles = nt; v.total_bases = r->total_bases;
+    v.codes = (const uint32_t*)c->codes.p; v.valid = (const uint32_t*)c->valid.p;
+    v.read_len = (const uint32_t*)c->read_len.p; v.read_blk = (const uint32_t*)c->read_blk.p;
+    v.tile_read = (const uint32_t*)c->tile_read.p; v.tile_blk = (const uint32_t*)c->tile_blk.p;
 
-    CTX_CUDA(cudaEventRecord(c->ev[0], st));
-    if ((rc = upload_reads(c, r))) return rc;
-    CTX_CUDA(cudaEventRecord(c->ev[1], st));
-    if (comp_counts && n) {
-        CTX_CUDA(cudaMemsetAsync(c->comp.p, 0, sizeof(uint32_t) * n * P, st));
-        if ((rc = lrb_dev_composition(&c->dview, k, (uint32_t*)c->comp.p, 0, r->n_tiles, st))) return rc;
+    // ---- chunk plan: cut at read boundaries, roughly equal numbers of blocks ---------------------------------
+    int n_chunks = 1;
+    {
+        const char* e = getenv("LRB_H2D_CHUNKS");
+        const int want = e && atoi(e) > 0 ? atoi(e) : 16;
+        n_chunks = (int)std::min<uint64_t>((uint64_t)std::min(want, LRB_PART_MAX_CHUNKS), std::max<uint64_t>(1, nb >> 16));
     }
-    CTX_CUDA(cudaEventRecord(c->ev[2], st));
+    std::vector<uint64_t> cr(n_chunks + 1), cb(n_chunks + 1), ct(n_chunks + 1);  // read / block / tile cut points
+    cr[0] = cb[0] = ct[0] = 0;
+    for (int i = 1; i < n_chunks; ++i) {
+        const uint32_t target = (uint32_t)(nb * (uint64_t)i / n_chunks);
+        uint64_t ri = (uint64_t)(std::upper_bound(r->read_blk, r->read_blk + n, target) - r->read_blk);
+        if (ri > 0) --ri;
+        ri = std::max(ri, cr[i - 1]);
+        cr[i] = ri;
+        cb[i] = r->read_blk[ri];
+        ct[i] = (uint64_t)(std::lower_bound(r->tile_read, r->tile_read + nt, (uint32_t)ri) - r->tile_read);
+    }
+    cr[n_chunks] = n; cb[n_chunks] = nb; ct[n_chunks] = nt;
+
+    // ---- go --------------------------------------------------------------------------------------------------
+    CTX_CUDA(cudaEventRecord(c->ev[0], st));
+    CTX_CUDA(cudaStreamWaitEvent(sin, c->ev[0], 0));
+    CTX_CUDA(cudaStreamWaitEvent(sout, c->ev[0], 0));
+    if (n) CTX_CUDA(cudaMemcpyAsync(c->read_len.p, r->read_len, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, sin));
+    CTX_CUDA(cudaMemcpyAsync(c->read_blk.p, r->read_blk, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, sin));
+    if (nt) {
+        CTX_CUDA(cudaMemcpyAsync(c->tile_read.p, r->tile_read, sizeof(uint32_t) * nt, cudaMemcpyHostToDevice, sin));
+        CTX_CUDA(cudaMemcpyAsync(c->tile_blk.p, r->tile_blk, sizeof(uint32_t) * nt, cudaMemcpyHostToDevice, sin));
+    }
+    CTX_CUDA(cudaEventRecord(c->sync_ev[0], sin));
+    for (int i = 0; i < n_chunks; ++i) {
+        const uint64_t b0 = cb[i], b1 = cb[i + 1];
+        const uint64_t w0 = 2 * b0, w1 = (i == n_chunks - 1) ? 2 * nb + 2 : 2 * b1;
+        const uint64_t v1 = (i == n_chunks - 1) ? nb + 1 : b1;
+        CTX_CUDA(cudaMemcpyAsync((uint32_t*)c->codes.p + w0, r->codes + w0, sizeof(uint32_t) * (w1 - w0), cudaMemcpyHostToDevice, sin));
+        CTX_CUDA(cudaMemcpyAsync((uint32_t*)c->valid.p + b0, r->valid + b0, sizeof(uint32_t) * (v1 - b0), cudaMemcpyHostToDevice, sin));
+        CTX_CUDA(cudaEventRecord(c->sync_ev[1 + i], sin));
+    }
+    CTX_CUDA(cudaEventRecord(c->ev[1], sin));  // H2D done
+
+    // compute stream: zero the outputs while the first chunk is in flight
+    if (comp_counts && n) CTX_CUDA(cudaMemsetAsync(c->comp.p, 0, sizeof(uint32_t) * n * P, st));
     if (do_search && n) {
         CTX_CUDA(cudaMemsetAsync(c->hist.p, 0, sizeof(uint32_t) * n * (size_t)bins, st));
         CTX_CUDA(cudaMemsetAsync(c->sums.p, 0, sizeof(uint32_t) * n, st));
@@ -214,40 +274,60 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         c->table_ready = false;
         CTX_CUDA(cudaMemsetAsync(c->table.p, 0, sizeof(uint32_t) * (size_t)kTableEntries, st));
     }
+    CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[0], 0));  // index arrays are on the device
     if (use_part) {
-        if (do_search && (rc = lrb_dev_fill_blk_read(&c->dview, (uint32_t*)c->blk_read.p, st))) return rc;
-        if ((rc = lrb_dev_partition_build(&c->dview, (const uint32_t*)c->blk_read.p, do_search ? 1 : 0, 0, r->n_blocks, 0, kTableEntries,
-                                          bucket_shift, &c->part, st)))
-            return rc;
+        if (do_search && (rc = lrb_dev_fill_blk_read(&v, (uint32_t*)c->blk_read.p, st))) return rc;
+        if ((rc = lrb_dev_partition_begin(&c->part, do_search ? 1 : 0, 0, kTableEntries, bucket_shift, st))) return rc;
+    }
+    for (int i = 0; i < n_chunks; ++i) {
+        CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[1 + i], 0));
+        if (comp_counts && n && (rc = lrb_dev_composition(&v, k, (uint32_t*)c->comp.p, ct[i], ct[i + 1], st))) return rc;
+        if (use_part) {
+            if ((rc = lrb_dev_partition_add(&v, (const uint32_t*)c->blk_read.p, cb[i], cb[i + 1], &c->part, st))) return rc;
+        } else if (do_count) {
+            if ((rc = lrb_dev_count(&v, (uint32_t*)c->table.p, cb[i], cb[i + 1], 0, kTableEntries, st))) return rc;
+        }
+    }
+    CTX_CUDA(cudaEventRecord(c->ev[2], st));  // composition (+ partition) of every chunk done
+    if (comp_counts && n) {                   // composition rows go home while the table passes run
+        CTX_CUDA(cudaStreamWaitEvent(sout, c->ev[2], 0));
+        CTX_CUDA(cudaMemcpyAsync(comp_counts, c->comp.p, sizeof(uint32_t) * n * P, cudaMemcpyDeviceToHost, sout));
+    }
+    CTX_CUDA(cudaEventRecord(c->sync_ev[LRB_PART_MAX_CHUNKS + 1], sout));
+    if (use_part) {
         const int mode = (do_count ? 1 : 0) | (do_search && n ? 2 : 0);
         if (mode && (rc = lrb_dev_partition_apply(&c->part, mode, (uint32_t*)c->table.p, bin_size, bins, (uint32_t*)c->hist.p,
                                                   (uint32_t*)c->sums.p, st)))
             return rc;
-    } else if (do_count) {
-        if ((rc = lrb_dev_count(&c->dview, (uint32_t*)c->table.p, 0, r->n_blocks, 0, kTableEntries, st))) return rc;
     }
-    CTX_CUDA(cudaEventRecord(c->ev[3], st));
+    CTX_CUDA(cudaEventRecord(c->ev[3], st));  // table passes done
     if (do_count) {
         if ((rc = lrb_dev_mirror((uint32_t*)c->table.p, st))) return rc;
         c->table_ready = true;
     }
     CTX_CUDA(cudaEventRecord(c->ev[4], st));
     if (!use_part && do_search && n) {
-        if ((rc = lrb_dev_search(&c->dview, (const uint32_t*)c->table.p, bin_size, bins, (uint32_t*)c->hist.p,
-                                 (uint32_t*)c->sums.p, 0, r->n_tiles, 0, kTableEntries, st)))
+        if ((rc = lrb_dev_search(&v, (const uint32_t*)c->table.p, bin_size, bins, (uint32_t*)c->hist.p, (uint32_t*)c->sums.p, 0, nt, 0,
+                                 kTableEntries, st)))
             return rc;
     }
     CTX_CUDA(cudaEventRecord(c->ev[5], st));
-    if (comp_counts && n) CTX_CUDA(cudaMemcpyAsync(comp_counts, c->comp.p, sizeof(uint32_t) * n * P, cudaMemcpyDeviceToHost, st));
     if (do_search && n) {
         CTX_CUDA(cudaMemcpyAsync(cov_hist, c->hist.p, sizeof(uint32_t) * n * (size_t)bins, cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaMemcpyAsync(cov_sums, c->sums.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     }
     if (table_host) CTX_CUDA(cudaMemcpyAsync(table_host, c->table.p, sizeof(uint32_t) * (size_t)kTableEntries, cudaMemcpyDeviceToHost, st));
+    CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[LRB_PART_MAX_CHUNKS + 1], 0));  // join the composition D2H
     CTX_CUDA(cudaEventRecord(c->ev[6], st));
     CTX_CUDA(cudaStreamSynchronize(st));
+    CTX_CUDA(cudaStreamSynchronize(sin));
+    CTX_CUDA(cudaStreamSynchronize(sout));
     CTX_CUDA(cudaGetLastError());
-    for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&c->ms[i], c->ev[i], c->ev[i + 1]);
+    // [0] h2d (copy stream) [1] composition+partition (until the last chunk is processed) [2] table passes
+    // [3] mirror [4] direct search [5] result D2H tail [6] whole call
+    cudaEventElapsedTime(&c->ms[0], c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->ms[1], c->ev[0], c->ev[2]);
+    for (int i = 2; i < 6; ++i) cudaEventElapsedTime(&c->ms[i], c->ev[i], c->ev[i + 1]);
     cudaEventElapsedTime(&c->ms[6], c->ev[0], c->ev[6]);
     return LRB_OK;
 }

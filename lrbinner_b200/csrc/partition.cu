@@ -1,22 +1,26 @@
 // partition.cu — L2-resident 15-mer table passes (count and search) via one key-partition of the windows.
 //
 // Why (measured on this pool's B200, profiles/r01_ubench_roofline.jsonl): uniform-random RED.ADD.U32 runs at
-// 20 G/s over a 4 GiB table (every update misses L2: 32 B sector in, 32 B out) but at ~190 G/s when the
-// touched slice is <= 64 MiB; random 4 B gathers: 38-48 G/s vs 288 G/s.  The direct kernels
-// (kernels.cu: k_count15 / k_search15) sit exactly on the DRAM-random numbers.  Here the valid windows are
-// first partitioned by the high bits of their bit-15-clear key into buckets whose table slice (2^25 keys =
-// 128 MiB of addresses, 64 MiB touched because bit 15 is clear) fits the 126 MB L2; then, bucket by bucket,
-// the keys are streamed back (coalesced) and applied to the resident slice:
+// 20 G/s over a 4 GiB table (every update misses L2: a sector pair in, a sector out) but at ~190 G/s when
+// the touched slice is <= 64 MiB; random 4 B gathers: 38-48 G/s vs 288 G/s.  The direct kernels
+// (kernels.cu: k_count15 / k_search15) sit exactly on the DRAM-random numbers (profiles/r01_bench_n1_v0_*).
+// Here the valid windows are first partitioned by the high bits of their bit-15-clear key into buckets whose
+// table slice (2^24 keys = 64 MiB of addresses, 32 MiB touched because bit 15 is clear) fits the 126 MB L2
+// together with the histogram rows; then, bucket by bucket, the lists are streamed back (coalesced) and
+// applied to the resident slice:
 //
-//   k_bucket_hist   one scan: windows per bucket                                   (sizes the regions exactly)
-//   k_partition     one scan: (key[, read id]) -> bucket regions; per 8192-slot CTA chunk the entries are
-//                   ranked with shared-memory atomics, staged in shared memory and copied out as contiguous
-//                   runs, so global writes are coalesced
+//   k_bucket_hist   one scan of a chunk of the stream: windows per bucket           (sizes the regions exactly)
+//   k_chunk_scan    device-side exclusive scan -> region offsets of the chunk       (no host round trip)
+//   k_partition     second scan: (key[, read id]) -> bucket regions; per 8192-slot CTA step the entries are
+//                   ranked with shared-memory atomics, staged in shared memory and copied out bucket by
+//                   bucket as contiguous runs, so global writes are coalesced
 //   k_count_keys    per bucket: RED.ADD.U32 table[key]                              (L2-resident atomics)
-//   k_search_keys   per bucket: count = table[key] (L2 hit, right after the bucket was counted), bucket rule,
-//                   run-length aggregation of equal (read, bin) neighbours, RED into hist[read][bin] / sums
+//   k_search_keys   per bucket: count = table[key] (an L2 hit), bucket rule, run-length aggregation of equal
+//                   (read, bin) neighbours, RED into hist[read][bin] / sums[read]
 //
-// Results are bit-identical to the direct kernels: the same windows, the same keys, integer sums.
+// The stream can be added in several chunks (lrb_dev_partition_add), each with its own regions, so the
+// partition of chunk i overlaps the host-to-device copy of chunk i+1; everything is asynchronous on the
+// caller's stream.  Results are bit-identical to the direct kernels: same windows, same keys, integer sums.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,9 +34,22 @@ using namespace lrb;
 
 namespace {
 
-constexpr int kPartThreads = 256;          // one 32-slot block per thread -> 8192 slots per CTA chunk
+constexpr int kPartThreads = 256;          // one 32-slot block per thread -> 8192 slots per CTA step
 constexpr int kChunkSlots = kPartThreads * 32;
-constexpr int kMaxBuckets = 64;
+constexpr int kMaxBuckets = LRB_PART_MAX_BUCKETS;
+constexpr int kMaxChunks = LRB_PART_MAX_CHUNKS;
+typedef unsigned long long ull;
+
+// device-side bookkeeping, lives in lrb_partition.small (LRB_PART_SMALL_U64 u64)
+struct PartMeta {
+    ull counts[kMaxChunks][kMaxBuckets];   // entries of (chunk, bucket)
+    ull offsets[kMaxChunks][kMaxBuckets];  // first entry of (chunk, bucket) in keys[] / rids[]
+    ull cursor[kMaxChunks][kMaxBuckets];   // fill cursors used by k_partition
+    ull chunk_base[kMaxChunks + 1];        // first entry of each chunk's region
+    ull needed;                            // entries the chunks added so far need in total
+    ull overflow;                          // != 0: capacity exceeded, lists are incomplete (apply does nothing)
+};
+static_assert(sizeof(PartMeta) <= sizeof(ull) * LRB_PART_SMALL_U64, "lrb_partition.small too small");
 
 __global__ void __launch_bounds__(256) k_fill_blk_read(lrb_reads_view R, uint32_t* __restrict__ blk_read) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -65,7 +82,7 @@ __device__ __forceinline__ BlockWindows load_block(const uint32_t* __restrict__ 
 // windows per bucket (bucket = key >> shift, numbered from bucket0 = key_lo >> shift)
 __global__ void __launch_bounds__(256)
 k_bucket_hist(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, uint64_t blk_lo, uint64_t blk_hi,
-              uint32_t key_lo, uint32_t key_hi, int shift, unsigned long long* __restrict__ counts) {
+              uint32_t key_lo, uint32_t key_hi, int shift, ull* __restrict__ counts) {
     __shared__ uint32_t s_cnt[kMaxBuckets];
     if (threadIdx.x < kMaxBuckets) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -79,37 +96,68 @@ k_bucket_hist(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ v
         });
     }
     __syncthreads();
-    if (threadIdx.x < kMaxBuckets && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    if (threadIdx.x < kMaxBuckets && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (ull)s_cnt[threadIdx.x]);
 }
 
-// (key[, read]) of every valid window -> its bucket's region, coalesced through a shared-memory stage
-template <bool WITH_RID>
-__global__ void __launch_bounds__(kPartThreads, 2)
-k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
-            uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb,
-            const unsigned long long* __restrict__ offsets, unsigned long long* __restrict__ cursor,
-            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rids_out) {
-    extern __shared__ uint32_t s_stage[];  // keys[kChunkSlots] (+ rids[kChunkSlots])
-    __shared__ uint32_t s_cnt[kMaxBuckets], s_base[kMaxBuckets + 1];
-    __shared__ unsigned long long s_gbase[kMaxBuckets];
-    uint32_t* stage_key = s_stage;
-    uint32_t* stage_rid = s_stage + kChunkSlots;
-    const uint32_t bucket0 = key_lo >> shift;
-    const int tid = threadIdx.x;
-    const uint64_t n_chunks = (blk_hi - blk_lo + kPartThreads - 1) / kPartThreads;
+// one warp: offsets of chunk c = chunk_base[c] + exclusive scan of its bucket counts; guards the capacity
+__global__ void k_chunk_scan(PartMeta* __restrict__ m, int c, int nb, ull capacity) {
+    const int lane = threadIdx.x;
+    const ull c0 = (lane < nb) ? m->counts[c][lane] : 0ull;
+    const ull c1 = (lane + 32 < nb) ? m->counts[c][lane + 32] : 0ull;
+    ull x0 = c0, x1 = c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const ull y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d);
+        if (lane >= d) { x0 += y0; x1 += y1; }
+    }
+    const ull tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
+    const ull total = tot0 + __shfl_sync(0xFFFFFFFFu, x1, 31);
+    const ull base = m->chunk_base[c];
+    const bool fits = (m->overflow == 0) && (base + total <= capacity);
+    __syncwarp();
+    m->offsets[c][lane] = base + x0 - c0;
+    m->offsets[c][lane + 32] = base + tot0 + x1 - c1;
+    if (!fits) {  // keep the lists consistent (this chunk contributes nothing) and remember how much was needed
+        m->counts[c][lane] = 0;
+        m->counts[c][lane + 32] = 0;
+    }
+    if (lane == 0) {
+        m->needed += total;
+        m->chunk_base[c + 1] = fits ? base + total : base;
+        if (!fits) m->overflow = 1;
+    }
+}
 
-    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+// (key[, read]) of every valid window of the chunk -> its bucket's region, coalesced through a shared-memory stage
+template <bool WITH_RID>
+__global__ void __launch_bounds__(kPartThreads, 3)
+k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
+            uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb, PartMeta* __restrict__ meta,
+            int c, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rids_out) {
+    __shared__ uint32_t s_key[kChunkSlots];   // staged keys, grouped by bucket
+    __shared__ uint8_t s_tid[kChunkSlots];    // which thread (hence which read) staged the entry
+    __shared__ uint32_t s_rid[kPartThreads];
+    __shared__ uint32_t s_cnt[kMaxBuckets], s_base[kMaxBuckets];
+    __shared__ ull s_gbase[kMaxBuckets];
+    if (meta->overflow) return;
+    const ull* __restrict__ offsets = meta->offsets[c];
+    ull* __restrict__ cursor = meta->cursor[c];
+    const uint32_t bucket0 = key_lo >> shift;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t n_steps = (blk_hi - blk_lo + kPartThreads - 1) / kPartThreads;
+
+    for (uint64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
         if (tid < kMaxBuckets) s_cnt[tid] = 0;
         __syncthreads();
-        const uint64_t gb = blk_lo + chunk * kPartThreads + tid;
+        const uint64_t gb = blk_lo + step * kPartThreads + tid;
         uint32_t key[32];
         uint32_t posw[16];  // rank inside the CTA's bucket run, two 16-bit values per word
-        uint32_t m = 0, rid = 0;
+        uint32_t m = 0;
         if (gb < blk_hi) {
             const BlockWindows b = load_block(codes, valid, gb);
             m = b.m;
             if (m) {
-                if (WITH_RID) rid = __ldg(blk_read + gb);
+                if (WITH_RID) s_rid[tid] = __ldg(blk_read + gb);
                 const uint32_t r0 = rc16(b.w1), r1 = rc16(b.w0), r2 = rc16(b.pw);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -129,21 +177,20 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
             }
         }
         __syncthreads();
-        if (tid < 32) {  // exclusive scan of the bucket counts (nb <= 64: two per lane) + global reservation
-            const uint32_t c0 = (tid < nb) ? s_cnt[tid] : 0u;
-            const uint32_t c1 = (tid + 32 < nb) ? s_cnt[tid + 32] : 0u;
+        if (warp == 0) {  // exclusive scan of the bucket counts (nb <= 64: two per lane) + global reservation
+            const uint32_t c0 = (lane < nb) ? s_cnt[lane] : 0u;
+            const uint32_t c1 = (lane + 32 < nb) ? s_cnt[lane + 32] : 0u;
             uint32_t x0 = c0, x1 = c1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d);
-                if (tid >= d) { x0 += y0; x1 += y1; }
+                if (lane >= d) { x0 += y0; x1 += y1; }
             }
             const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
-            s_base[tid] = x0 - c0;
-            s_base[tid + 32] = tot0 + x1 - c1;
-            if (tid == 31) s_base[kMaxBuckets] = tot0 + x1;
-            if (tid < nb && c0) s_gbase[tid] = offsets[tid] + atomicAdd(&cursor[tid], (unsigned long long)c0);
-            if (tid + 32 < nb && c1) s_gbase[tid + 32] = offsets[tid + 32] + atomicAdd(&cursor[tid + 32], (unsigned long long)c1);
+            s_base[lane] = x0 - c0;
+            s_base[lane + 32] = tot0 + x1 - c1;
+            if (lane < nb && c0) s_gbase[lane] = offsets[lane] + atomicAdd(&cursor[lane], (ull)c0);
+            if (lane + 32 < nb && c1) s_gbase[lane + 32] = offsets[lane + 32] + atomicAdd(&cursor[lane + 32], (ull)c1);
         }
         __syncthreads();
         if (m) {
@@ -151,69 +198,81 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
             for (int j = 0; j < 32; ++j) {
                 if ((m >> j) & 1u) {
                     const uint32_t idx = s_base[(key[j] >> shift) - bucket0] + ((posw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-                    stage_key[idx] = key[j];
-                    if (WITH_RID) stage_rid[idx] = rid;
+                    s_key[idx] = key[j];
+                    if (WITH_RID) s_tid[idx] = (uint8_t)tid;
                 }
             }
         }
         __syncthreads();
-        const uint32_t total = s_base[kMaxBuckets];
-        for (uint32_t i = tid; i < total; i += kPartThreads) {
-            const uint32_t kk = stage_key[i];
-            const uint32_t b = (kk >> shift) - bucket0;
-            const unsigned long long dst = s_gbase[b] + (i - s_base[b]);
-            __stcs(keys_out + dst, kk);
-            if (WITH_RID) __stcs(rids_out + dst, stage_rid[i]);
+        for (int b = warp; b < nb; b += kPartThreads / 32) {  // each warp copies whole bucket runs: contiguous both sides
+            const uint32_t cnt = s_cnt[b];
+            if (!cnt) continue;
+            const uint32_t beg = s_base[b];
+            const ull g = s_gbase[b];
+            for (uint32_t i = lane; i < cnt; i += 32) {
+                __stcs(keys_out + g + i, s_key[beg + i]);
+                if (WITH_RID) __stcs(rids_out + g + i, s_rid[s_tid[beg + i]]);
+            }
         }
         __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_count_keys(const uint32_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ table) {
+k_count_keys(const uint32_t* __restrict__ keys, const PartMeta* __restrict__ meta, int bucket, int n_chunks,
+             uint32_t* __restrict__ table) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n; i += 4 * stride) {
-        const uint32_t k0 = __ldcs(keys + i), k1 = __ldcs(keys + i + stride), k2 = __ldcs(keys + i + 2 * stride),
-                       k3 = __ldcs(keys + i + 3 * stride);
-        atomicAdd(table + k0, 1u);
-        atomicAdd(table + k1, 1u);
-        atomicAdd(table + k2, 1u);
-        atomicAdd(table + k3, 1u);
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint64_t n = meta->counts[c][bucket];
+        const uint32_t* __restrict__ kk = keys + meta->offsets[c][bucket];
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride) {
+            const uint32_t k0 = __ldcs(kk + i), k1 = __ldcs(kk + i + stride), k2 = __ldcs(kk + i + 2 * stride),
+                           k3 = __ldcs(kk + i + 3 * stride);
+            atomicAdd(table + k0, 1u);
+            atomicAdd(table + k1, 1u);
+            atomicAdd(table + k2, 1u);
+            atomicAdd(table + k3, 1u);
+        }
+        for (; i < n; i += stride) atomicAdd(table + __ldcs(kk + i), 1u);
     }
-    for (; i < n; i += stride) atomicAdd(table + __ldcs(keys + i), 1u);
 }
 
 // entries of one bucket: hist[read][bin(table[key])] += 1, sums[read] += 1, aggregated over runs of equal neighbours
 __global__ void __launch_bounds__(256)
-k_search_keys(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rids, uint64_t n,
-              const uint32_t* __restrict__ table, uint32_t S32, uint64_t magic, uint32_t B, uint32_t* __restrict__ hist,
-              uint32_t* __restrict__ sums) {
+k_search_keys(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rids, const PartMeta* __restrict__ meta,
+              int bucket, int n_chunks, const uint32_t* __restrict__ table, uint32_t S32, uint64_t magic, uint32_t B,
+              uint32_t* __restrict__ hist, uint32_t* __restrict__ sums) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += stride) {
-        const bool act = i < n;
-        const uint32_t key = act ? __ldcs(keys + i) : 0u;
-        const uint32_t rid = act ? __ldcs(rids + i) : 0xFFFFFFFFu;
-        const uint32_t cnt = act ? table[key] : 0u;  // written by k_count_keys just before: an L2 hit
-        const uint32_t bin = coverage_bin(cnt, S32, magic, B);
-        const unsigned long long tag = act ? (((unsigned long long)rid << 12) | bin) : ~0ull;
-        const unsigned long long ptag = __shfl_up_sync(0xFFFFFFFFu, tag, 1);
-        const uint32_t prid = __shfl_up_sync(0xFFFFFFFFu, rid, 1);
-        const bool head = (lane == 0) || (tag != ptag);
-        const bool head_r = (lane == 0) || (rid != prid);
-        const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
-        const uint32_t heads_r = __ballot_sync(0xFFFFFFFFu, head_r);
-        const uint32_t above = ~((2u << lane) - 1u);  // lanes above this one (lane 31: none)
-        if (act && head) {
-            const uint32_t nx = heads & above;
-            const uint32_t run = (nx ? (uint32_t)__ffs(nx) - 1u : 32u) - lane;
-            atomicAdd(hist + (size_t)rid * B + bin, run);
-        }
-        if (act && head_r) {
-            const uint32_t nx = heads_r & above;
-            const uint32_t run = (nx ? (uint32_t)__ffs(nx) - 1u : 32u) - lane;
-            atomicAdd(sums + rid, run);
+    const uint32_t above = ~((2u << lane) - 1u);  // lanes above this one (lane 31: none)
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint64_t n = meta->counts[c][bucket];
+        const uint64_t off = meta->offsets[c][bucket];
+        const uint32_t* __restrict__ kk = keys + off;
+        const uint32_t* __restrict__ rr = rids + off;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += stride) {
+            const bool act = i < n;
+            const uint32_t key = act ? __ldcs(kk + i) : 0u;
+            const uint32_t rid = act ? __ldcs(rr + i) : 0xFFFFFFFFu;
+            const uint32_t cnt = act ? table[key] : 0u;  // slice resident in L2 (just counted, or warmed by earlier gathers)
+            const uint32_t bin = act ? coverage_bin(cnt, S32, magic, B) : 0xFFFFu;
+            const uint32_t prid = __shfl_up_sync(0xFFFFFFFFu, rid, 1);
+            const uint32_t pbin = __shfl_up_sync(0xFFFFFFFFu, bin, 1);
+            const bool head_r = (lane == 0) || (rid != prid);
+            const bool head = head_r || (bin != pbin);
+            const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+            const uint32_t heads_r = __ballot_sync(0xFFFFFFFFu, head_r);
+            if (act && head) {
+                const uint32_t nx = heads & above;
+                const uint32_t run = (nx ? (uint32_t)__ffs(nx) - 1u : 32u) - lane;
+                atomicAdd(hist + (size_t)rid * B + bin, run);
+            }
+            if (act && head_r) {
+                const uint32_t nx = heads_r & above;
+                const uint32_t run = (nx ? (uint32_t)__ffs(nx) - 1u : 32u) - lane;
+                atomicAdd(sums + rid, run);
+            }
         }
     }
 }
@@ -235,14 +294,12 @@ extern "C" int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_re
     return LRB_OK;
 }
 
-// ---- host side: build the partition once, then count and/or search bucket by bucket ---------------------------
-extern "C" int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t* blk_read, int with_rids, uint64_t blk_lo,
-                                       uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
-                                       lrb_partition* part, void* stream) {
-    if (!dev || !part || !part->keys || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_build: null argument");
-    if (with_rids && (!part->rids || !blk_read)) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_build: read ids need part->rids and blk_read");
+// ---- host side: begin, add chunk(s) of the stream, then count and/or search bucket by bucket -------------------
+extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint32_t key_lo, uint32_t key_hi,
+                                       int log2_bucket_keys, void* stream) {
+    if (!part || !part->keys || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_begin: null argument");
+    if (with_rids && !part->rids) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_begin: read ids need part->rids");
     if (key_hi > kTableEntries) key_hi = kTableEntries;
-    if (blk_hi > dev->n_blocks) blk_hi = dev->n_blocks;
     const int shift = log2_bucket_keys;
     if (shift < 20 || shift > 30) return lrb_set_error(LRB_EINVAL, "log2_bucket_keys must be in [20, 30]");
     const uint32_t bsz = 1u << shift;
@@ -253,43 +310,63 @@ extern "C" int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t
     part->n_buckets = nb;
     part->shift = shift;
     part->key_lo = key_lo;
+    part->key_hi = key_hi;
     part->has_rids = with_rids ? 1 : 0;
-    for (int b = 0; b <= kMaxBuckets; ++b) part->offset[b] = 0;
-    for (int b = 0; b < kMaxBuckets; ++b) part->count[b] = 0;
+    part->n_chunks = 0;
+    LRB_CUDA(cudaMemsetAsync(part->small, 0, sizeof(PartMeta), (cudaStream_t)stream));
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_partition_add(const lrb_reads_view* dev, const uint32_t* blk_read, uint64_t blk_lo, uint64_t blk_hi,
+                                     lrb_partition* part, void* stream) {
+    if (!dev || !part || !part->keys || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_add: null argument");
+    if (part->has_rids && !blk_read) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_add: read ids need blk_read");
+    if (blk_hi > dev->n_blocks) blk_hi = dev->n_blocks;
     if (blk_lo >= blk_hi) return LRB_OK;
+    if (part->n_chunks >= kMaxChunks) return lrb_set_error(LRB_EINVAL, "too many chunks in one partition (max %d)", kMaxChunks);
+    const int c = part->n_chunks++;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long* d_counts = part->small;                    // [64]
-    unsigned long long* d_offsets = part->small + kMaxBuckets;     // [64]
-    unsigned long long* d_cursor = part->small + 2 * kMaxBuckets;  // [64]
-    LRB_CUDA(cudaMemsetAsync(part->small, 0, sizeof(unsigned long long) * 3 * kMaxBuckets, st));
+    PartMeta* meta = reinterpret_cast<PartMeta*>(part->small);
     const uint64_t nblk = blk_hi - blk_lo;
     const int nsm = sms();
+    const int nb = part->n_buckets, shift = part->shift;
     {
         const uint64_t want = (nblk + 255) / 256;
         const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)nsm * 8);
-        k_bucket_hist<<<grid, 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, key_lo, key_hi, shift, d_counts);
-        LRB_CUDA(cudaGetLastError());
+        k_bucket_hist<<<grid, 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, &meta->counts[c][0]);
+        k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity);
     }
-    LRB_CUDA(cudaMemcpyAsync(part->count, d_counts, sizeof(unsigned long long) * kMaxBuckets, cudaMemcpyDeviceToHost, st));
-    LRB_CUDA(cudaStreamSynchronize(st));  // the one host round trip: region sizes
-    for (int b = 0; b < kMaxBuckets; ++b) part->offset[b + 1] = part->offset[b] + (b < nb ? part->count[b] : 0ull);
-    const unsigned long long total = part->offset[nb];
-    if (total > part->capacity)
-        return lrb_set_error(LRB_ENOMEM, "partition workspace too small: %llu entries needed, %llu available", total, (unsigned long long)part->capacity);
-    LRB_CUDA(cudaMemcpyAsync(d_offsets, part->offset, sizeof(unsigned long long) * kMaxBuckets, cudaMemcpyHostToDevice, st));
-    const uint64_t n_chunks = (nblk + kPartThreads - 1) / kPartThreads;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)nsm * 16);
-    if (with_rids) {
-        const size_t smem = sizeof(uint32_t) * 2 * kChunkSlots;
-        LRB_CUDA(cudaFuncSetAttribute(k_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_partition<true><<<grid, kPartThreads, smem, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, key_lo, key_hi, shift, nb,
-                                                              d_offsets, d_cursor, part->keys, part->rids);
-    } else {
-        const size_t smem = sizeof(uint32_t) * kChunkSlots;
-        k_partition<false><<<grid, kPartThreads, smem, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, key_lo, key_hi, shift, nb,
-                                                               d_offsets, d_cursor, part->keys, part->rids);
-    }
+    const uint64_t n_steps = (nblk + kPartThreads - 1) / kPartThreads;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_steps, (uint64_t)nsm * 24);
+    if (part->has_rids)
+        k_partition<true><<<grid, kPartThreads, 0, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, part->key_lo, part->key_hi,
+                                                           shift, nb, meta, c, part->keys, part->rids);
+    else
+        k_partition<false><<<grid, kPartThreads, 0, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, part->key_lo, part->key_hi,
+                                                            shift, nb, meta, c, part->keys, part->rids);
     LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+// One-shot convenience: begin + a single chunk.
+extern "C" int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t* blk_read, int with_rids, uint64_t blk_lo,
+                                       uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
+                                       lrb_partition* part, void* stream) {
+    int rc = lrb_dev_partition_begin(part, with_rids, key_lo, key_hi, log2_bucket_keys, stream);
+    if (rc) return rc;
+    return lrb_dev_partition_add(dev, blk_read, blk_lo, blk_hi, part, stream);
+}
+
+// Synchronises the stream and reports whether the lists are complete; *needed = entries required in total.
+extern "C" int lrb_dev_partition_check(const lrb_partition* part, uint64_t* needed, void* stream) {
+    if (!part || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_check: null argument");
+    ull h[2] = {0, 0};
+    const PartMeta* meta = reinterpret_cast<const PartMeta*>(part->small);
+    LRB_CUDA(cudaMemcpyAsync(h, &meta->needed, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LRB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (needed) *needed = h[0];
+    if (h[1])
+        return lrb_set_error(LRB_ENOMEM, "partition workspace too small: %llu entries needed, %llu available", h[0], (ull)part->capacity);
     return LRB_OK;
 }
 
@@ -304,17 +381,15 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
         if (bin_size <= 0) return lrb_set_error(LRB_EINVAL, "bin_size must be >= 1 (the reference divides by it)");
         if (bins <= 0 || bins > LRB_MAX_BINS) return lrb_set_error(LRB_EINVAL, "bins must be in [1, %d]", LRB_MAX_BINS);
     }
+    if (part->n_chunks == 0) return LRB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t S32 = bin_size > 0xFFFFFFFFl ? 0xFFFFFFFFu : (uint32_t)(bin_size > 0 ? bin_size : 1);
     const uint64_t magic = coverage_magic(S32);
-    const int nsm = sms();
+    const PartMeta* meta = reinterpret_cast<const PartMeta*>(part->small);
+    const unsigned grid = (unsigned)sms() * 8;
     for (int b = 0; b < part->n_buckets; ++b) {
-        const uint64_t n = part->count[b];
-        if (!n) continue;
-        const uint32_t* kb = part->keys + part->offset[b];
-        const unsigned grid = (unsigned)std::min<uint64_t>((n + 1023) / 1024, (uint64_t)nsm * 8);
-        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(kb, n, table);
-        if (do_search) k_search_keys<<<grid, 256, 0, st>>>(kb, part->rids + part->offset[b], n, table, S32, magic, (uint32_t)bins, hist, sums);
+        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, table);
+        if (do_search) k_search_keys<<<grid, 256, 0, st>>>(part->keys, part->rids, meta, b, part->n_chunks, table, S32, magic, (uint32_t)bins, hist, sums);
     }
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;

@@ -58,6 +58,7 @@ class CudaEngine:
         self._rb = None
         self.ws = profile.PartitionWorkspace(device_reads, capacity=workspace_entries)
         self._rect = None
+        self._verified = set()
 
     def zeros(self, shape):
         return self.torch.zeros(shape, dtype=self.torch.int32, device=self.device)
@@ -74,7 +75,8 @@ class CudaEngine:
             shift = self.shift
             while (key_hi - key_lo) >> shift > 64:
                 shift += 1
-            self.ws.build(True, blo, bhi, key_lo, key_hi, shift, grow=True)
+            self.ws.build(True, blo, bhi, key_lo, key_hi, shift, grow=rect not in self._verified)
+            self._verified.add(rect)       # same reads, same rectangle -> same size: later steps stay asynchronous
             self._rect = rect
 
     def composition(self, k, comp, read_lo, read_hi):

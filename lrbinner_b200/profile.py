@@ -138,7 +138,9 @@ class Context:
     def timings(self):
         ms = (C.c_float * 7)()
         check(lib.lrb_ctx_last_timings(self._h, ms))
-        return dict(zip(("h2d", "composition", "count", "mirror", "search", "d2h", "total"), [float(x) for x in ms]))
+        # phases overlap (3-stream pipeline): h2d runs beside composition+partition; "total" is the whole call
+        return dict(zip(("h2d", "composition_partition", "table_passes", "mirror", "search_direct", "d2h_tail", "total"),
+                        [float(x) for x in ms]))
 
     def table_load(self, path):
         check(lib.lrb_ctx_table_load(self._h, str(path).encode()))
@@ -252,40 +254,53 @@ class PartitionWorkspace:
     def __init__(self, dr, capacity=None, with_rids=True):
         torch = dr.torch
         self.dr = dr
-        self.capacity = int(capacity if capacity is not None else max(dr.total_bases, 1))
+        self.capacity = int(capacity if capacity is not None else max(dr.n_blocks * 32, 1))
         self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
         self.rids = torch.empty(self.capacity, dtype=torch.int32, device=dr.device) if with_rids else None
-        self.small = torch.zeros(256, dtype=torch.int64, device=dr.device)
+        self.small = torch.zeros(_lib.PART_SMALL_U64, dtype=torch.int64, device=dr.device)
         self.blk_read = torch.empty(max(dr.n_blocks, 1), dtype=torch.int32, device=dr.device)
         check(lib.lrb_dev_fill_blk_read(C.byref(dr.view), C.c_void_p(self.blk_read.data_ptr()), _stream()))
         self.part = _lib.Partition(keys=self.keys.data_ptr(), rids=self.rids.data_ptr() if with_rids else None,
                                    small=self.small.data_ptr(), capacity=self.capacity)
 
+    def begin(self, with_rids=True, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24):
+        check(lib.lrb_dev_partition_begin(C.byref(self.part), 1 if with_rids else 0, key_lo, min(key_hi, _lib.TABLE_ENTRIES),
+                                          log2_bucket_keys, _stream()))
+
+    def add(self, blk_lo=0, blk_hi=None):
+        check(lib.lrb_dev_partition_add(C.byref(self.dr.view), C.c_void_p(self.blk_read.data_ptr()), blk_lo,
+                                        self.dr.n_blocks if blk_hi is None else blk_hi, C.byref(self.part), _stream()))
+
     def build(self, with_rids=True, blk_lo=0, blk_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, grow=False):
-        args = (C.byref(self.dr.view), C.c_void_p(self.blk_read.data_ptr()), 1 if with_rids else 0, blk_lo,
-                self.dr.n_blocks if blk_hi is None else blk_hi, key_lo, min(key_hi, _lib.TABLE_ENTRIES), log2_bucket_keys,
-                C.byref(self.part), _stream())
-        rc = lib.lrb_dev_partition_build(*args)
-        if rc == _lib.LRB_ENOMEM and grow:      # the exact pre-pass told us the size: grow the lists once and retry
-            torch = self.dr.torch
-            need = int(self.part.offset[self.part.n_buckets])
-            self.keys = self.rids = None
-            torch.cuda.empty_cache()
-            self.capacity = need + need // 64 + 1024
-            self.keys = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
-            self.rids = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
-            self.part.keys, self.part.rids, self.part.capacity = self.keys.data_ptr(), self.rids.data_ptr(), self.capacity
-            rc = lib.lrb_dev_partition_build(*args)
-        check(rc)
+        self.begin(with_rids, key_lo, key_hi, log2_bucket_keys)
+        self.add(blk_lo, blk_hi)
+        if grow:      # verify (synchronises); if the lists did not fit, the device told us the size: grow once and redo
+            needed = C.c_uint64(0)
+            rc = lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream())
+            if rc == _lib.LRB_ENOMEM:
+                torch = self.dr.torch
+                self.keys = self.rids = None
+                torch.cuda.empty_cache()
+                self.capacity = int(needed.value) + int(needed.value) // 64 + 1024
+                self.keys = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
+                self.rids = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
+                self.part.keys, self.part.rids, self.part.capacity = self.keys.data_ptr(), self.rids.data_ptr(), self.capacity
+                self.begin(with_rids, key_lo, key_hi, log2_bucket_keys)
+                self.add(blk_lo, blk_hi)
+                rc = lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream())
+            check(rc)
+
+    def check(self):
+        """Synchronises; raises LrbError(LRB_ENOMEM) if the lists overflowed `capacity`. Returns entries needed."""
+        needed = C.c_uint64(0)
+        check(lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream()))
+        return int(needed.value)
 
     def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None):
         mode = (1 if count else 0) | (2 if search else 0)
         check(lib.lrb_dev_partition_apply(C.byref(self.part), mode, C.c_void_p(table.data_ptr()), bin_size, bins,
                                           C.c_void_p(hist.data_ptr()) if hist is not None else None,
                                           C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream()))
-
-    def total_entries(self):
-        return int(self.part.offset[self.part.n_buckets])
 
 
 def dev_table15_partitioned(dr, ws, table, do_count=True, bin_size=1, bins=1, hist=None, sums=None, blk_lo=0, blk_hi=None,

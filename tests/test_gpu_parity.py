@@ -308,8 +308,23 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     assert torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
     # workspace too small is an error, not a truncation
     small = PartitionWorkspace(dr, capacity=1000)
+    t_small = z(2 ** 30)
+    dev_table15_partitioned(dr, small, t_small, True)
     with pytest.raises(_lib.LrbError):
-        dev_table15_partitioned(dr, small, z(2 ** 30), True)
+        small.check()
+    assert int(t_small.count_nonzero().item()) == 0          # an overflowing chunk is dropped as a whole, never half-applied
+    small.build(True, grow=True)                              # grows to the size the device reported
+    small.apply(t_small, count=True)
+    assert torch.equal(t_small, table_d)
+    # chunked adds (as the H2D pipeline does) give the same lists' effect
+    table_p, hist_p, sums_p = z(2 ** 30), z(n, bc), z(n)
+    ws.begin(True)
+    cuts = [0, nb // 7, nb // 2, nb - 3, nb]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        ws.add(lo, hi)
+    ws.apply(table_p, True, True, bs, bc, hist_p, sums_p)
+    assert ws.check() == int(sums_d.to(torch.int64).sum().item())
+    assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
 
 
 # ---- full-size properties (BASELINE.json configs) ---------------------------------------------------------
