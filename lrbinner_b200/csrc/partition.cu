@@ -129,7 +129,7 @@ __global__ void k_chunk_scan(PartMeta* __restrict__ m, int c, int nb, ull capaci
 }
 
 // (key[, read]) of every valid window of the chunk -> its bucket's region, coalesced through a shared-memory stage
-template <bool WITH_RID>
+template <bool WITH_RID, bool FULL>
 __global__ void __launch_bounds__(kPartThreads, 3)
 k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
             uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb, PartMeta* __restrict__ meta,
@@ -159,18 +159,28 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
             if (m) {
                 if (WITH_RID) s_rid[tid] = __ldg(blk_read + gb);
                 const uint32_t r0 = rc16(b.w1), r1 = rc16(b.w0), r2 = rc16(b.pw);
+                if (FULL && m == 0xFFFFFFFFu) {  // interior block of a read, whole key space: no predicates at all
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if ((j & 1) == 0) posw[j >> 1] = 0;
-                    key[j] = 0;
-                    if ((m >> j) & 1u) {
+                    for (int j = 0; j < 32; ++j) {
                         const uint32_t kk = canonical15(kmer_ending_at<15>(b.pw, b.w0, b.w1, j), rc15_ending_at(r0, r1, r2, j));
-                        if (kk >= key_lo && kk < key_hi) {
-                            key[j] = kk;
-                            const uint32_t p = atomicAdd(&s_cnt[(kk >> shift) - bucket0], 1u);
-                            posw[j >> 1] |= p << (16 * (j & 1));
-                        } else {
-                            m &= ~(1u << j);
+                        key[j] = kk;
+                        const uint32_t p = atomicAdd(&s_cnt[kk >> shift], 1u);
+                        if (j & 1) posw[j >> 1] |= p << 16; else posw[j >> 1] = p;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((j & 1) == 0) posw[j >> 1] = 0;
+                        key[j] = 0;
+                        if ((m >> j) & 1u) {
+                            const uint32_t kk = canonical15(kmer_ending_at<15>(b.pw, b.w0, b.w1, j), rc15_ending_at(r0, r1, r2, j));
+                            if (FULL || (kk >= key_lo && kk < key_hi)) {
+                                key[j] = kk;
+                                const uint32_t p = atomicAdd(&s_cnt[(kk >> shift) - bucket0], 1u);
+                                posw[j >> 1] |= p << (16 * (j & 1));
+                            } else {
+                                m &= ~(1u << j);
+                            }
                         }
                     }
                 }
@@ -193,7 +203,14 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
             if (lane + 32 < nb && c1) s_gbase[lane + 32] = offsets[lane + 32] + atomicAdd(&cursor[lane + 32], (ull)c1);
         }
         __syncthreads();
-        if (m) {
+        if (m == 0xFFFFFFFFu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t idx = s_base[(key[j] >> shift) - bucket0] + ((j & 1) ? (posw[j >> 1] >> 16) : (posw[j >> 1] & 0xFFFFu));
+                s_key[idx] = key[j];
+                if (WITH_RID) s_tid[idx] = (uint8_t)tid;
+            }
+        } else if (m) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if ((m >> j) & 1u) {
@@ -245,7 +262,6 @@ k_search_keys(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ri
               uint32_t* __restrict__ hist, uint32_t* __restrict__ sums) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint32_t above = ~((2u << lane) - 1u);  // lanes above this one (lane 31: none)
     for (int c = 0; c < n_chunks; ++c) {
         const uint64_t n = meta->counts[c][bucket];
         const uint64_t off = meta->offsets[c][bucket];
@@ -257,21 +273,13 @@ k_search_keys(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ ri
             const uint32_t rid = act ? __ldcs(rr + i) : 0xFFFFFFFFu;
             const uint32_t cnt = act ? table[key] : 0u;  // slice resident in L2 (just counted, or warmed by earlier gathers)
             const uint32_t bin = act ? coverage_bin(cnt, S32, magic, B) : 0xFFFFu;
-            const uint32_t prid = __shfl_up_sync(0xFFFFFFFFu, rid, 1);
-            const uint32_t pbin = __shfl_up_sync(0xFFFFFFFFu, bin, 1);
-            const bool head_r = (lane == 0) || (rid != prid);
-            const bool head = head_r || (bin != pbin);
-            const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
-            const uint32_t heads_r = __ballot_sync(0xFFFFFFFFu, head_r);
-            if (act && head) {
-                const uint32_t nx = heads & above;
-                const uint32_t run = (nx ? (uint32_t)__ffs(nx) - 1u : 32u) - lane;
-                atomicAdd(hist + (size_t)rid * B + bin, run);
-            }
-            if (act && head_r) {
-                const uint32_t nx = heads_r & above;
-                const uint32_t run = (nx ? (uint32_t)__ffs(nx) - 1u : 32u) - lane;
-                atomicAdd(sums + rid, run);
+            // one RED per distinct (read, bin) and one per distinct read in the warp: consecutive list entries come from
+            // the same few reads and bins, and the L1/LSU sector rate (gather + REDs) is what bounds this kernel
+            const uint32_t m_r = __match_any_sync(0xFFFFFFFFu, rid);
+            const uint32_t m_g = m_r & __match_any_sync(0xFFFFFFFFu, bin);
+            if (act) {
+                if ((uint32_t)__ffs(m_g) - 1u == lane) atomicAdd(hist + (size_t)rid * B + bin, (uint32_t)__popc(m_g));
+                if ((uint32_t)__ffs(m_r) - 1u == lane) atomicAdd(sums + rid, (uint32_t)__popc(m_r));
             }
         }
     }
@@ -338,12 +346,13 @@ extern "C" int lrb_dev_partition_add(const lrb_reads_view* dev, const uint32_t* 
     }
     const uint64_t n_steps = (nblk + kPartThreads - 1) / kPartThreads;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_steps, (uint64_t)nsm * 24);
-    if (part->has_rids)
-        k_partition<true><<<grid, kPartThreads, 0, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, part->key_lo, part->key_hi,
-                                                           shift, nb, meta, c, part->keys, part->rids);
-    else
-        k_partition<false><<<grid, kPartThreads, 0, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, part->key_lo, part->key_hi,
-                                                            shift, nb, meta, c, part->keys, part->rids);
+    const bool full = part->key_lo == 0 && part->key_hi >= kTableEntries;
+#define LRB_LAUNCH_PART(RID, FULLK)                                                                                              \
+    k_partition<RID, FULLK><<<grid, kPartThreads, 0, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, part->key_lo, part->key_hi, \
+                                                           shift, nb, meta, c, part->keys, part->rids)
+    if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
+    else { if (full) LRB_LAUNCH_PART(false, true); else LRB_LAUNCH_PART(false, false); }
+#undef LRB_LAUNCH_PART
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
