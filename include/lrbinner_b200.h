@@ -75,6 +75,15 @@ int lrb_reads_from_lengths(const uint32_t* lengths, uint64_t n_reads, lrb_reads*
 int lrb_reads_view_get(const lrb_reads* r, lrb_reads_view* view);  /* host pointers */
 /* Copy read i back out as ASCII from the packed form ('A','C','T','G' by code; lossy for non-ACGT). */
 int lrb_reads_unpack(const lrb_reads* r, uint64_t i, char* dst, uint64_t cap);
+/* (Re)build the list of validity exceptions from the current `valid` words: the blocks whose valid word is not the
+ * one implied by the read length alone (every in-read slot an uppercase ACGT).  The file/ASCII constructors do this
+ * while packing; call it after filling codes/valid of a lrb_reads_from_lengths layout by hand.  With the list in
+ * place lrb_profile_host ships only codes + exceptions (0.25 B/base) and rebuilds `valid` on the device.
+ * *n_exceptions (may be NULL) receives the list length. */
+int lrb_reads_index_valid(lrb_reads* r, int threads, uint64_t* n_exceptions);
+/* The current exception list (host pointers owned by `r`; *n = 0 and NULLs when none was built):
+ * valid[blk[i]] == word[i] != the word implied by the read length, blk ascending. */
+int lrb_reads_exceptions(const lrb_reads* r, const uint32_t** blk, const uint32_t** word, uint64_t* n);
 void lrb_reads_free(lrb_reads* r);
 
 /* ------------------------------------------------------------------------------------------------
@@ -97,6 +106,11 @@ int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_t blk_lo, u
                   uint32_t key_lo, uint32_t key_hi, void* stream);
 int lrb_dev_mirror(uint32_t* table, void* stream);
 
+/* valid[] of `dev` from the read lengths alone (all in-read slots valid, padding slots invalid), then
+ * valid[exc_blk[i]] = exc_valid[i] for the n_exc exception blocks (device arrays; may be NULL when n_exc == 0). */
+int lrb_dev_fill_valid(const lrb_reads_view* dev, const uint32_t* exc_blk, const uint32_t* exc_valid, uint64_t n_exc,
+                       void* stream);
+
 /* line_to_vec (kmer_utils.h:24-87): hist[N*bins] += bucket counts, sums[N] += valid windows, for the
  * reads of tiles [tile_lo, tile_hi).  With key range [0, 2^30) every valid window looks up table[val]
  * (forward key; the table must be mirrored).  With a narrower range (key-sharded search) only windows
@@ -108,30 +122,42 @@ int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_si
 
 /* L2-resident variant of count and search (csrc/partition.cu).  The valid windows whose bit-15-clear key lies
  * in [key_lo, key_hi) are partitioned ONCE by key >> log2_bucket_keys into at most 64 buckets (key range
- * bucket-aligned) as (key[, read index]) lists; lrb_dev_partition_apply then walks the buckets and applies each
- * list to the table slice while that slice is resident in L2:
+ * bucket-aligned, 20 <= log2_bucket_keys <= 25) as lists of 4-byte entries (key inside the bucket + read index
+ * relative to the entry's 8192-slot step); lrb_dev_partition_apply then walks the buckets and applies each list to
+ * the table slice while that slice is resident in L2:
  *   mode 1  count : table[key] += 1                    (== lrb_dev_count; mirror separately)
- *   mode 2  search: hist/sums through table[key]       (== lrb_dev_search on bit-15-clear keys; no mirror needed)
+ *   mode 2  search: hist/sums through table[key]       (== lrb_dev_search on bit-15-clear keys; no mirror needed);
+ *                   sums[r] is rewritten as the sum of hist row r for r < n_reads (hist and sums must have been
+ *                   zeroed together and only ever updated by lrb_dev_search / this call)
  *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
  * begin() resets the lists; add() appends the windows of blocks [blk_lo, blk_hi) as one chunk (up to 64 chunks,
  * e.g. one per host-to-device copy so partitioning overlaps the transfer); build() = begin + one add.  A
  * partition can be applied several times (count, exchange tables between GPUs, then search).  Everything is
- * asynchronous on `stream`; sizes are computed on the device.  If the lists would exceed `capacity` the chunk is
- * dropped and a device flag is raised: lrb_dev_partition_check (synchronises) returns LRB_ENOMEM and the number
- * of entries needed.  capacity >= total number of slots can never overflow.
+ * asynchronous on `stream`; sizes are computed on the device and the list layout is deterministic.  If the lists
+ * would exceed `capacity` the chunk is dropped and a device flag is raised: apply then does nothing and
+ * lrb_dev_partition_check (synchronises) returns LRB_ENOMEM and the number of entries needed.
+ * capacity >= total number of slots can never overflow.
  * blk_read[n_blocks] = read index of every block (lrb_dev_fill_blk_read).  The caller owns the device buffers and
- * fills keys/rids/small/capacity; the library fills the rest.  Bit-identical to the direct kernels. */
+ * fills keys/small/steps/capacity/step_capacity; the library fills the rest.  `steps` holds the per-step tables:
+ * lrb_partition_steps_words(step_capacity) u32 words, step_capacity >= lrb_partition_step_capacity(n_blocks,
+ * number of add() calls).  Bit-identical to the direct kernels. */
 #define LRB_PART_MAX_BUCKETS 64
 #define LRB_PART_MAX_CHUNKS 64
+#define LRB_PART_MAX_GROUPS 8192
 #define LRB_PART_SMALL_U64 16384
 typedef struct {
     uint32_t* keys;                /* device, capacity entries */
-    uint32_t* rids;                /* device, capacity entries (NULL if never searching) */
     unsigned long long* small;     /* device scratch, LRB_PART_SMALL_U64 u64 */
+    uint32_t* steps;               /* device, lrb_partition_steps_words(step_capacity) u32 */
     uint64_t capacity;
+    uint64_t step_capacity;
+    uint64_t steps_used, n_reads;
     int n_buckets, shift, has_rids, n_chunks;
     uint32_t key_lo, key_hi;
+    uint32_t chunk_step0[LRB_PART_MAX_CHUNKS], chunk_nsteps[LRB_PART_MAX_CHUNKS];
 } lrb_partition;
+uint64_t lrb_partition_step_capacity(uint64_t n_blocks, int max_chunks);
+uint64_t lrb_partition_steps_words(uint64_t step_capacity);
 int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_read, void* stream);
 int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint32_t key_lo, uint32_t key_hi, int log2_bucket_keys,
                             void* stream);

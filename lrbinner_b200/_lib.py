@@ -30,9 +30,11 @@ class ReadsView(C.Structure):
 
 class Partition(C.Structure):
     """lrb_partition: caller-owned device buffers + the bucket layout filled by lrb_dev_partition_begin/add."""
-    _fields_ = [("keys", C.c_void_p), ("rids", C.c_void_p), ("small", C.c_void_p), ("capacity", C.c_uint64),
+    _fields_ = [("keys", C.c_void_p), ("small", C.c_void_p), ("steps", C.c_void_p), ("capacity", C.c_uint64),
+                ("step_capacity", C.c_uint64), ("steps_used", C.c_uint64), ("n_reads", C.c_uint64),
                 ("n_buckets", C.c_int), ("shift", C.c_int), ("has_rids", C.c_int), ("n_chunks", C.c_int),
-                ("key_lo", C.c_uint32), ("key_hi", C.c_uint32)]
+                ("key_lo", C.c_uint32), ("key_hi", C.c_uint32),
+                ("chunk_step0", C.c_uint32 * 64), ("chunk_nsteps", C.c_uint32 * 64)]
 
 
 PART_SMALL_U64 = 16384
@@ -60,12 +62,17 @@ _SIG = {
     "lrb_reads_view_get": (C.c_int, [_P, C.POINTER(ReadsView)]),
     "lrb_reads_unpack": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "lrb_reads_free": (None, [_P]),
+    "lrb_reads_index_valid": (C.c_int, [_P, C.c_int, _P]),
+    "lrb_reads_exceptions": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "lrb_dev_fill_valid": (C.c_int, [C.POINTER(ReadsView), _P, _P, C.c_uint64, _P]),
     "lrb_dev_composition": (C.c_int, [C.POINTER(ReadsView), C.c_int, _P, C.c_uint64, C.c_uint64, _P]),
     "lrb_dev_count": (C.c_int, [C.POINTER(ReadsView), _P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_mirror": (C.c_int, [_P, _P]),
     "lrb_dev_search": (C.c_int, [C.POINTER(ReadsView), _P, C.c_long, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
                                  C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_fill_blk_read": (C.c_int, [C.POINTER(ReadsView), _P, _P]),
+    "lrb_partition_step_capacity": (C.c_uint64, [C.c_uint64, C.c_int]),
+    "lrb_partition_steps_words": (C.c_uint64, [C.c_uint64]),
     "lrb_dev_partition_begin": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, C.c_int, _P]),
     "lrb_dev_partition_add": (C.c_int, [C.POINTER(ReadsView), _P, C.c_uint64, C.c_uint64, _P, _P]),
     "lrb_dev_partition_check": (C.c_int, [_P, _P, _P]),

@@ -74,7 +74,8 @@ struct lrb_ctx {
     cudaEvent_t sync_ev[LRB_PART_MAX_CHUNKS + 2] = {};  // [0] index arrays, [1..] H2D chunks, [last] composition D2H
     DevBuf codes, valid, read_len, read_blk, tile_read, tile_blk;
     DevBuf table, comp, hist, sums, text;
-    DevBuf part_keys, part_rids, part_small, blk_read;  // L2-resident (partitioned) table passes
+    DevBuf part_keys, part_small, part_steps, blk_read;  // L2-resident (partitioned) table passes
+    DevBuf exc_blk, exc_valid;                            // validity exceptions (lrb_dev_fill_valid)
     lrb_partition part = {};
     bool table_ready = false;  // holds a complete (mirrored) table
     lrb_reads_view dview = {};
@@ -119,7 +120,7 @@ extern "C" void lrb_ctx_destroy(lrb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->codes, &c->valid, &c->read_len, &c->read_blk, &c->tile_read, &c->tile_blk, &c->table, &c->comp,
-                      &c->hist, &c->sums, &c->text, &c->part_keys, &c->part_rids, &c->part_small, &c->blk_read})
+                      &c->hist, &c->sums, &c->text, &c->part_keys, &c->part_small, &c->part_steps, &c->blk_read, &c->exc_blk, &c->exc_valid})
         b->release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->sync_ev) if (ev) cudaEventDestroy(ev);
@@ -189,8 +190,20 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         if ((rc = c->sums.reserve(std::max<size_t>(16, sizeof(uint32_t) * n)))) return rc;
     }
     if ((do_count || do_search) && (rc = c->table.reserve(sizeof(uint32_t) * (size_t)kTableEntries))) return rc;
+    // validity bitmap: when the reads carry their exception list (blocks whose valid word is not implied by the read
+    // length) and it is short, only codes + exceptions cross PCIe (0.25 instead of 0.375 B/base) and the bitmap is
+    // rebuilt on the device; LRB_SHIP_VALID=1 forces the plain copy.
+    bool ship_valid = !(r->exc_ready && r->n_exc <= nb / 16);
+    {
+        const char* e = getenv("LRB_SHIP_VALID");
+        if (e && atoi(e) > 0) ship_valid = true;
+    }
+    if (!ship_valid) {
+        if ((rc = c->exc_blk.reserve(sizeof(uint32_t) * (r->n_exc + 1)))) return rc;
+        if ((rc = c->exc_valid.reserve(sizeof(uint32_t) * (r->n_exc + 1)))) return rc;
+    }
     // table passes: key-partitioned + L2-resident (csrc/partition.cu) unless LRB_TABLE_PATH=direct or its
-    // workspace (8 B per slot) does not fit; the direct kernels (one random HBM access per window) remain as
+    // workspace (4 B per slot) does not fit; the direct kernels (one random HBM access per window) remain as
     // the small-memory GPU path.  Both are bit-identical.
     bool use_part = (do_count || do_search) && nb > 0;
     {
@@ -200,21 +213,23 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
     int bucket_shift = 24;
     {
         const char* e = getenv("LRB_BUCKET_LOG2");
-        if (e && atoi(e) >= 24 && atoi(e) <= 30) bucket_shift = atoi(e);
+        if (e && atoi(e) >= 24 && atoi(e) <= 25) bucket_shift = atoi(e);
     }
     if (use_part) {
         const size_t cap = std::max<uint64_t>(nb * 32, 1);  // >= number of slots: the lists can never overflow
-        if (c->part_keys.reserve(sizeof(uint32_t) * cap) || (do_search && c->part_rids.reserve(sizeof(uint32_t) * cap)) ||
+        const uint64_t step_cap = lrb_partition_step_capacity(nb, LRB_PART_MAX_CHUNKS);
+        if (c->part_keys.reserve(sizeof(uint32_t) * cap) || c->part_steps.reserve(sizeof(uint32_t) * lrb_partition_steps_words(step_cap)) ||
             c->part_small.reserve(sizeof(unsigned long long) * LRB_PART_SMALL_U64) || c->blk_read.reserve(sizeof(uint32_t) * (nb + 1))) {
             cudaGetLastError();
             c->part_keys.release();
-            c->part_rids.release();
+            c->part_steps.release();
             use_part = false;
         } else {
             c->part.keys = (uint32_t*)c->part_keys.p;
-            c->part.rids = do_search ? (uint32_t*)c->part_rids.p : nullptr;
+            c->part.steps = (uint32_t*)c->part_steps.p;
             c->part.small = (unsigned long long*)c->part_small.p;
             c->part.capacity = cap;
+            c->part.step_capacity = step_cap;
         }
     }
     lrb_reads_view& v = c->dview;
@@ -253,13 +268,18 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         CTX_CUDA(cudaMemcpyAsync(c->tile_read.p, r->tile_read, sizeof(uint32_t) * nt, cudaMemcpyHostToDevice, sin));
         CTX_CUDA(cudaMemcpyAsync(c->tile_blk.p, r->tile_blk, sizeof(uint32_t) * nt, cudaMemcpyHostToDevice, sin));
     }
+    if (!ship_valid && r->n_exc) {
+        CTX_CUDA(cudaMemcpyAsync(c->exc_blk.p, r->exc_blk, sizeof(uint32_t) * r->n_exc, cudaMemcpyHostToDevice, sin));
+        CTX_CUDA(cudaMemcpyAsync(c->exc_valid.p, r->exc_valid, sizeof(uint32_t) * r->n_exc, cudaMemcpyHostToDevice, sin));
+    }
     CTX_CUDA(cudaEventRecord(c->sync_ev[0], sin));
     for (int i = 0; i < n_chunks; ++i) {
         const uint64_t b0 = cb[i], b1 = cb[i + 1];
         const uint64_t w0 = 2 * b0, w1 = (i == n_chunks - 1) ? 2 * nb + 2 : 2 * b1;
         const uint64_t v1 = (i == n_chunks - 1) ? nb + 1 : b1;
         CTX_CUDA(cudaMemcpyAsync((uint32_t*)c->codes.p + w0, r->codes + w0, sizeof(uint32_t) * (w1 - w0), cudaMemcpyHostToDevice, sin));
-        CTX_CUDA(cudaMemcpyAsync((uint32_t*)c->valid.p + b0, r->valid + b0, sizeof(uint32_t) * (v1 - b0), cudaMemcpyHostToDevice, sin));
+        if (ship_valid)
+            CTX_CUDA(cudaMemcpyAsync((uint32_t*)c->valid.p + b0, r->valid + b0, sizeof(uint32_t) * (v1 - b0), cudaMemcpyHostToDevice, sin));
         CTX_CUDA(cudaEventRecord(c->sync_ev[1 + i], sin));
     }
     CTX_CUDA(cudaEventRecord(c->ev[1], sin));  // H2D done
@@ -274,7 +294,8 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         c->table_ready = false;
         CTX_CUDA(cudaMemsetAsync(c->table.p, 0, sizeof(uint32_t) * (size_t)kTableEntries, st));
     }
-    CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[0], 0));  // index arrays are on the device
+    CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[0], 0));  // index arrays (and validity exceptions) are on the device
+    if (!ship_valid && (rc = lrb_dev_fill_valid(&v, (const uint32_t*)c->exc_blk.p, (const uint32_t*)c->exc_valid.p, r->n_exc, st))) return rc;
     if (use_part) {
         if (do_search && (rc = lrb_dev_fill_blk_read(&v, (uint32_t*)c->blk_read.p, st))) return rc;
         if ((rc = lrb_dev_partition_begin(&c->part, do_search ? 1 : 0, 0, kTableEntries, bucket_shift, st))) return rc;

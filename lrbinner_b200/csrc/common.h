@@ -27,6 +27,13 @@ struct lrb_reads {
     uint32_t* tile_read = nullptr;  // n_tiles
     uint32_t* tile_blk = nullptr;   // n_tiles
     bool pinned = false;            // buffers came from cudaHostAlloc
+    // validity exceptions: blocks whose valid word differs from the one implied by the read length (all in-read
+    // slots valid).  Lets the host path ship 0.25 B/base instead of 0.375: the device rebuilds `valid` from
+    // read_len and patches these blocks (lrb_dev_fill_valid).
+    uint64_t n_exc = 0;
+    uint32_t* exc_blk = nullptr;    // n_exc, ascending
+    uint32_t* exc_valid = nullptr;  // n_exc
+    bool exc_pinned = false, exc_ready = false;
 };
 
 // page-locked when a CUDA device is usable, plain aligned memory otherwise (host-only unit tests)

@@ -183,6 +183,8 @@ static void free_reads(lrb_reads* r) {
     free(r->read_blk);
     free(r->tile_read);
     free(r->tile_blk);
+    lrb_host_free(r->exc_blk, r->exc_pinned);
+    lrb_host_free(r->exc_valid, r->exc_pinned);
     delete r;
 }
 
@@ -257,7 +259,76 @@ static void pack_all(lrb_reads* r, int threads, GetSeq get) {
     for (auto& th : pool) th.join();
 }
 
+// exception list = blocks whose valid word differs from default_valid (threads scan disjoint read ranges, in order)
+static int index_valid(lrb_reads* r, int threads) {
+    lrb_host_free(r->exc_blk, r->exc_pinned);
+    lrb_host_free(r->exc_valid, r->exc_pinned);
+    r->exc_blk = r->exc_valid = nullptr;
+    r->n_exc = 0;
+    r->exc_ready = false;
+    const uint64_t n = r->n_reads;
+    threads = std::max(1, std::min(threads, 64));
+    if (n < 64) threads = 1;
+    std::vector<std::vector<uint32_t>> found(threads);  // (block, word) pairs
+    auto work = [&](int t, uint64_t lo, uint64_t hi) {
+        std::vector<uint32_t>& f = found[t];
+        for (uint64_t i = lo; i < hi; ++i) {
+            const uint32_t b0 = r->read_blk[i], b1 = r->read_blk[i + 1], len = r->read_len[i];
+            for (uint32_t b = b0; b < b1; ++b) {
+                const uint32_t v = r->valid[b];
+                if (v != lrb::default_valid_word(len, (uint64_t)(b - b0) * 32)) { f.push_back(b); f.push_back(v); }
+            }
+        }
+    };
+    if (threads == 1) work(0, 0, n);
+    else {
+        std::vector<std::thread> pool;
+        uint64_t lo = 0;
+        for (int t = 0; t < threads; ++t) {
+            const uint64_t target = r->n_blocks * (uint64_t)(t + 1) / threads;
+            uint64_t hi = (t == threads - 1) ? n : (uint64_t)(std::upper_bound(r->read_blk, r->read_blk + n, (uint32_t)target) - r->read_blk);
+            hi = std::min(std::max(hi, lo), n);
+            pool.emplace_back(work, t, lo, hi);
+            lo = hi;
+        }
+        for (auto& th : pool) th.join();
+    }
+    uint64_t total = 0;
+    for (auto& f : found) total += f.size() / 2;
+    bool p1 = false, p2 = false;
+    r->exc_blk = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (total + 1), &p1);
+    r->exc_valid = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (total + 1), &p2);
+    if (!r->exc_blk || !r->exc_valid || p1 != p2) {
+        lrb_host_free(r->exc_blk, p1);
+        lrb_host_free(r->exc_valid, p2);
+        r->exc_blk = r->exc_valid = nullptr;
+        return lrb_set_error(LRB_ENOMEM, "out of memory (validity exceptions)");
+    }
+    r->exc_pinned = p1;
+    uint64_t k = 0;
+    for (auto& f : found)
+        for (size_t j = 0; j < f.size(); j += 2) { r->exc_blk[k] = f[j]; r->exc_valid[k] = f[j + 1]; ++k; }
+    r->n_exc = total;
+    r->exc_ready = true;
+    return LRB_OK;
+}
+
 }  // namespace
+
+extern "C" int lrb_reads_index_valid(lrb_reads* r, int threads, uint64_t* n_exceptions) {
+    if (!r) return lrb_set_error(LRB_EINVAL, "lrb_reads_index_valid: null argument");
+    const int rc = index_valid(r, threads);
+    if (!rc && n_exceptions) *n_exceptions = r->n_exc;
+    return rc;
+}
+
+extern "C" int lrb_reads_exceptions(const lrb_reads* r, const uint32_t** blk, const uint32_t** word, uint64_t* n) {
+    if (!r || !blk || !word || !n) return lrb_set_error(LRB_EINVAL, "lrb_reads_exceptions: null argument");
+    *blk = r->exc_ready ? r->exc_blk : nullptr;
+    *word = r->exc_ready ? r->exc_valid : nullptr;
+    *n = r->exc_ready ? r->n_exc : 0;
+    return LRB_OK;
+}
 
 extern "C" int lrb_reads_from_file(const char* path, int threads, lrb_reads** out) {
     if (!path || !out) return lrb_set_error(LRB_EINVAL, "lrb_reads_from_file: null argument");
@@ -276,6 +347,7 @@ extern "C" int lrb_reads_from_file(const char* path, int threads, lrb_reads** ou
     if (rc) { free_reads(r); return rc; }
     const unsigned char* pool = (const unsigned char*)parsed.pool.data();
     pack_all(r, threads, [&](uint64_t i) { return pool + parsed.recs[i].off; });
+    if ((rc = index_valid(r, threads))) { free_reads(r); return rc; }
     *out = r;
     return LRB_OK;
 }
@@ -296,6 +368,7 @@ extern "C" int lrb_reads_from_ascii(const char* bases, const uint64_t* offsets, 
     int rc = build_layout(r);
     if (rc) { free_reads(r); return rc; }
     pack_all(r, threads, [&](uint64_t i) { return (const unsigned char*)bases + offsets[i]; });
+    if ((rc = index_valid(r, threads))) { free_reads(r); return rc; }
     *out = r;
     return LRB_OK;
 }

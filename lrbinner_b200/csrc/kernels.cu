@@ -115,6 +115,22 @@ __global__ void __launch_bounds__(256) k_mirror(uint32_t* __restrict__ table) {
     for (uint32_t a = ty; a < 64; a += 4) table[mirror_dst_index(t, a, tx)] = tile[rc_small(tx, 3)][rc_small(a, 3)];
 }
 
+// validity bitmap from the read lengths (one warp per read), then the sparse exceptions on top
+__global__ void __launch_bounds__(256) k_default_valid(lrb_reads_view R, uint32_t* __restrict__ valid) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R.n_reads) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t b0 = R.read_blk[r], b1 = R.read_blk[r + 1], len = R.read_len[r];
+    for (uint32_t b = b0 + lane; b < b1; b += 32) valid[b] = default_valid_word(len, (uint64_t)(b - b0) * 32);
+    if (r == R.n_reads - 1 && lane == 0) valid[R.n_blocks] = 0u;  // the word after the stream
+}
+
+__global__ void __launch_bounds__(256)
+k_patch_valid(const uint32_t* __restrict__ exc_blk, const uint32_t* __restrict__ exc_valid, uint64_t n_exc, uint32_t* __restrict__ valid) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_exc) valid[exc_blk[i]] = exc_valid[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // search: line_to_vec (kmer_utils.h:24-87)
 // ------------------------------------------------------------------------------------------------
@@ -311,6 +327,22 @@ extern "C" int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_
 extern "C" int lrb_dev_mirror(uint32_t* table, void* stream) {
     if (!table) return lrb_set_error(LRB_EINVAL, "lrb_dev_mirror: null table");
     k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_fill_valid(const lrb_reads_view* dev, const uint32_t* exc_blk, const uint32_t* exc_valid, uint64_t n_exc,
+                                  void* stream) {
+    if (!dev || !dev->valid || (n_exc && (!exc_blk || !exc_valid))) return lrb_set_error(LRB_EINVAL, "lrb_dev_fill_valid: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* valid = const_cast<uint32_t*>(dev->valid);
+    if (dev->n_reads) {
+        const uint64_t threads = dev->n_reads * 32;
+        k_default_valid<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(*dev, valid);
+    } else {
+        LRB_CUDA(cudaMemsetAsync(valid, 0, sizeof(uint32_t) * (dev->n_blocks + 1), st));
+    }
+    if (n_exc) k_patch_valid<<<(unsigned)((n_exc + 255) / 256), 256, 0, st>>>(exc_blk, exc_valid, n_exc, valid);
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

@@ -105,6 +105,13 @@ LRB_HD uint32_t window15_mask(uint32_t pv, uint32_t v) {
     return (uint32_t)(a >> 18);  // run starting at p = 32 + j - 14 ends at slot j
 }
 
+// valid word implied by the read length alone (every in-read slot an uppercase ACGT) for the block whose slot 0
+// is read position p0; blocks that differ are shipped as exceptions (ingest.cpp, lrb_dev_fill_valid).
+LRB_HD uint32_t default_valid_word(uint32_t len, uint64_t p0) {
+    const uint64_t n_in = len > p0 ? len - p0 : 0;
+    return n_in >= 32 ? 0xFFFFFFFFu : ((1u << (uint32_t)n_in) - 1u);
+}
+
 // The one key of {x, rc(x)} with bit 15 clear.  The middle base of a 15-mer sits at bits [14,15];
 // reverse complement maps it to its own complement (XOR 2), so exactly one of the pair has bit 15 == 0.
 // Every occurrence increments BOTH strands in the reference (kmer_utils.h:139-153), hence

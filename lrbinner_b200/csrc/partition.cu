@@ -7,16 +7,25 @@
 // Here the valid windows are first partitioned by the high bits of their bit-15-clear key into buckets whose
 // table slice (2^24 keys = 64 MiB of addresses, 32 MiB touched because bit 15 is clear) fits the 126 MB L2
 // together with the histogram rows; then, bucket by bucket, the lists are streamed back (coalesced) and
-// applied to the resident slice:
+// applied to the resident slice.
 //
-//   k_bucket_hist   one scan of a chunk of the stream: windows per bucket           (sizes the regions exactly)
-//   k_chunk_scan    device-side exclusive scan -> region offsets of the chunk       (no host round trip)
-//   k_partition     second scan: (key[, read id]) -> bucket regions; per 8192-slot CTA step the entries are
-//                   ranked with shared-memory atomics, staged in shared memory and copied out bucket by
-//                   bucket as contiguous runs, so global writes are coalesced
+// Layout of the lists (deterministic, no global cursors).  A STEP is 256 consecutive blocks (8192 slots) of a
+// chunk of the stream.  The windows of step s that fall into bucket b form a RUN; bucket b's region of the
+// chunk is the concatenation of its runs in step order.  One list entry is 4 bytes:
+//     entry = compact(key inside the bucket) | (read index - read index of the step's first block) << (shift-1)
+// compact() drops bit 15 (always 0 for the bit-15-clear key); a step spans at most 256 reads (every read owns at
+// least one block), so the read delta needs 8 bits and shift <= 25.
+//
+//   k_step_hist     one scan of the chunk: windows per (step, bucket) -> step_cnt (u16), per-group totals
+//   k_group_scan    per bucket: exclusive scan of the group totals, bucket total
+//   k_chunk_scan    region offsets of the chunk (exclusive scan over buckets), capacity guard
+//   k_partition     second scan: each CTA walks the steps of its group in order; the entries of a step are ranked
+//                   and placed in shared memory in ONE pass (the staging offsets are known from step_cnt), then
+//                   copied out run by run (contiguous on both sides); writes step_off[bucket][step]
 //   k_count_keys    per bucket: RED.ADD.U32 table[key]                              (L2-resident atomics)
-//   k_search_keys   per bucket: count = table[key] (an L2 hit), bucket rule, run-length aggregation of equal
-//                   (read, bin) neighbours, RED into hist[read][bin] / sums[read]
+//   k_search_keys   per bucket, warp per run: count = table[key] (an L2 hit), bucket rule, aggregation of equal
+//                   (read, bin) entries of the warp, RED into hist[read][bin]
+//   k_row_sums      sums[read] = sum of hist[read][*]  (every window lands in exactly one bin)
 //
 // The stream can be added in several chunks (lrb_dev_partition_add), each with its own regions, so the
 // partition of chunk i overlaps the host-to-device copy of chunk i+1; everything is asynchronous on the
@@ -34,22 +43,49 @@ using namespace lrb;
 
 namespace {
 
-constexpr int kPartThreads = 256;          // one 32-slot block per thread -> 8192 slots per CTA step
-constexpr int kChunkSlots = kPartThreads * 32;
+constexpr int kPartThreads = 256;          // one 32-slot block per thread -> 8192 slots per step
+constexpr int kStepSlots = kPartThreads * 32;
 constexpr int kMaxBuckets = LRB_PART_MAX_BUCKETS;
 constexpr int kMaxChunks = LRB_PART_MAX_CHUNKS;
+constexpr int kMaxGroups = LRB_PART_MAX_GROUPS;
+constexpr uint64_t kMaxChunkBlocks = 1ull << 26;  // 2^31 slots: run offsets inside a chunk's bucket region fit u32
 typedef unsigned long long ull;
 
 // device-side bookkeeping, lives in lrb_partition.small (LRB_PART_SMALL_U64 u64)
 struct PartMeta {
     ull counts[kMaxChunks][kMaxBuckets];   // entries of (chunk, bucket)
-    ull offsets[kMaxChunks][kMaxBuckets];  // first entry of (chunk, bucket) in keys[] / rids[]
-    ull cursor[kMaxChunks][kMaxBuckets];   // fill cursors used by k_partition
+    ull offsets[kMaxChunks][kMaxBuckets];  // first entry of (chunk, bucket) in keys[]
     ull chunk_base[kMaxChunks + 1];        // first entry of each chunk's region
     ull needed;                            // entries the chunks added so far need in total
     ull overflow;                          // != 0: capacity exceeded, lists are incomplete (apply does nothing)
 };
 static_assert(sizeof(PartMeta) <= sizeof(ull) * LRB_PART_SMALL_U64, "lrb_partition.small too small");
+
+// views into lrb_partition.steps (u32 words)
+struct StepTables {
+    uint32_t* grp_tot;    // [kMaxGroups][64]  windows of (group, bucket)                (re-used by every chunk)
+    uint32_t* grp_off;    // [kMaxGroups][64]  exclusive scan over groups
+    uint32_t* rid0;       // [cap]             read index of the step's first block
+    uint16_t* cnt;        // [cap][64]         windows of (step, bucket)
+    uint32_t* off;        // [64][cap]         first entry of run (bucket, step) inside the chunk's bucket region
+    uint64_t cap;
+};
+
+__host__ __device__ inline StepTables step_tables(uint32_t* steps, uint64_t cap) {
+    StepTables t;
+    t.cap = cap;
+    t.grp_tot = steps;
+    t.grp_off = t.grp_tot + (size_t)kMaxGroups * kMaxBuckets;
+    t.rid0 = t.grp_off + (size_t)kMaxGroups * kMaxBuckets;
+    t.cnt = reinterpret_cast<uint16_t*>(t.rid0 + cap);
+    t.off = t.rid0 + cap + cap * (kMaxBuckets / 2);
+    return t;
+}
+
+struct ChunkList {  // by-value kernel argument of the apply kernels
+    uint32_t step0[kMaxChunks];
+    uint32_t nsteps[kMaxChunks];
+};
 
 __global__ void __launch_bounds__(256) k_fill_blk_read(lrb_reads_view R, uint32_t* __restrict__ blk_read) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -79,24 +115,80 @@ __device__ __forceinline__ BlockWindows load_block(const uint32_t* __restrict__ 
     return b;
 }
 
-// windows per bucket (bucket = key >> shift, numbered from bucket0 = key_lo >> shift)
-__global__ void __launch_bounds__(256)
-k_bucket_hist(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, uint64_t blk_lo, uint64_t blk_hi,
-              uint32_t key_lo, uint32_t key_hi, int shift, ull* __restrict__ counts) {
-    __shared__ uint32_t s_cnt[kMaxBuckets];
-    if (threadIdx.x < kMaxBuckets) s_cnt[threadIdx.x] = 0;
+// f(key) for every window of the block whose bit-15-clear key lies in the partition's key range.  The common case
+// (every lane of the warp holds an interior block of a read, whole key space) runs without any predicate.
+template <bool FULL, class F>
+__device__ __forceinline__ void for_each_key(const BlockWindows& b, uint32_t key_lo, uint32_t key_hi, F f) {
+    const uint32_t r0 = rc16(b.w1), r1 = rc16(b.w0), r2 = rc16(b.pw);
+    if (FULL && __all_sync(0xFFFFFFFFu, b.m == 0xFFFFFFFFu)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f(canonical15(kmer_ending_at<15>(b.pw, b.w0, b.w1, j), rc15_ending_at(r0, r1, r2, j)));
+    } else if (__any_sync(0xFFFFFFFFu, b.m != 0u)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if ((b.m >> j) & 1u) {
+                const uint32_t kk = canonical15(kmer_ending_at<15>(b.pw, b.w0, b.w1, j), rc15_ending_at(r0, r1, r2, j));
+                if (FULL || (kk >= key_lo && kk < key_hi)) f(kk);
+            }
+        }
+    }
+}
+
+// ---- pass 1: windows per (step, bucket) --------------------------------------------------------------------
+// CTA g walks the steps [g*G, (g+1)*G) of the chunk.  s_cnt is double-buffered so one barrier per step suffices.
+template <bool FULL>
+__global__ void __launch_bounds__(kPartThreads)
+k_step_hist(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
+            uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, uint32_t n_steps, uint32_t G,
+            uint32_t step0, StepTables T) {
+    __shared__ uint32_t s_cnt[2][kMaxBuckets];
+    const int tid = threadIdx.x;
+    if (tid < 2 * kMaxBuckets) (&s_cnt[0][0])[tid] = 0;
     __syncthreads();
     const uint32_t bucket0 = key_lo >> shift;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t gb = blk_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < blk_hi; gb += stride) {
-        const BlockWindows b = load_block(codes, valid, gb);
-        if (!b.m) continue;
-        canon15_block(b.pw, b.w0, b.w1, b.m, [&](uint32_t key) {
-            if (key >= key_lo && key < key_hi) atomicAdd(&s_cnt[(key >> shift) - bucket0], 1u);
-        });
+    const uint32_t s_beg = blockIdx.x * G, s_end = min(n_steps, s_beg + G);
+    uint32_t run = 0;  // thread b < 64: windows of (this group, bucket b) so far
+    for (uint32_t s = s_beg; s < s_end; ++s) {
+        uint32_t* cnt = s_cnt[s & 1u];
+        const uint64_t gb = blk_lo + (uint64_t)s * kPartThreads + tid;
+        BlockWindows b;
+        b.m = b.pw = b.w0 = b.w1 = 0;
+        if (gb < blk_hi) b = load_block(codes, valid, gb);
+        for_each_key<FULL>(b, key_lo, key_hi, [&](uint32_t kk) { atomicAdd(&cnt[(kk >> shift) - bucket0], 1u); });
+        __syncthreads();
+        if (tid < kMaxBuckets) {
+            const uint32_t c = cnt[tid];
+            cnt[tid] = 0;  // next used at step s+2, after another barrier
+            T.cnt[(size_t)(step0 + s) * kMaxBuckets + tid] = (uint16_t)c;
+            run += c;
+        }
+        if (tid == kMaxBuckets && blk_read) T.rid0[step0 + s] = __ldg(blk_read + blk_lo + (uint64_t)s * kPartThreads);
     }
+    if (tid < kMaxBuckets) T.grp_tot[(size_t)blockIdx.x * kMaxBuckets + tid] = run;
+}
+
+// CTA b: grp_off[g][b] = exclusive scan over groups of grp_tot[g][b]; counts[c][b] = total
+__global__ void __launch_bounds__(256) k_group_scan(StepTables T, uint32_t n_groups, PartMeta* __restrict__ meta, int c) {
+    __shared__ ull s_part[256];
+    const uint32_t b = blockIdx.x, tid = threadIdx.x;
+    const uint32_t span = (n_groups + 255u) / 256u;
+    const uint32_t g0 = min(n_groups, tid * span), g1 = min(n_groups, g0 + span);
+    ull sum = 0;
+    for (uint32_t g = g0; g < g1; ++g) sum += T.grp_tot[(size_t)g * kMaxBuckets + b];
+    s_part[tid] = sum;
     __syncthreads();
-    if (threadIdx.x < kMaxBuckets && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (ull)s_cnt[threadIdx.x]);
+    for (int d = 1; d < 256; d <<= 1) {  // Hillis-Steele inclusive scan
+        const ull v = (tid >= (uint32_t)d) ? s_part[tid - d] : 0ull;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    ull acc = s_part[tid] - sum;
+    for (uint32_t g = g0; g < g1; ++g) {
+        T.grp_off[(size_t)g * kMaxBuckets + b] = (uint32_t)acc;  // < 2^31: a chunk has at most 2^31 slots
+        acc += T.grp_tot[(size_t)g * kMaxBuckets + b];
+    }
+    if (tid == 255) meta->counts[c][b] = s_part[255];
 }
 
 // one warp: offsets of chunk c = chunk_base[c] + exclusive scan of its bucket counts; guards the capacity
@@ -128,68 +220,39 @@ __global__ void k_chunk_scan(PartMeta* __restrict__ m, int c, int nb, ull capaci
     }
 }
 
-// (key[, read]) of every valid window of the chunk -> its bucket's region, coalesced through a shared-memory stage
+// ---- pass 2: entries -> bucket regions ---------------------------------------------------------------------
 template <bool WITH_RID, bool FULL>
-__global__ void __launch_bounds__(kPartThreads, 3)
+__global__ void __launch_bounds__(kPartThreads)
 k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
-            uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb, PartMeta* __restrict__ meta,
-            int c, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rids_out) {
-    __shared__ uint32_t s_key[kChunkSlots];   // staged keys, grouped by bucket
-    __shared__ uint8_t s_tid[kChunkSlots];    // which thread (hence which read) staged the entry
-    __shared__ uint32_t s_rid[kPartThreads];
-    __shared__ uint32_t s_cnt[kMaxBuckets], s_base[kMaxBuckets];
-    __shared__ ull s_gbase[kMaxBuckets];
+            uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb, uint32_t n_steps, uint32_t G,
+            uint32_t step0, StepTables T, const PartMeta* __restrict__ meta, int c, uint32_t* __restrict__ ent_out) {
+    __shared__ uint32_t s_ent[kStepSlots];                    // staged entries, grouped by bucket
+    __shared__ uint32_t s_cur[kMaxBuckets];                   // staging cursor of each bucket
+    __shared__ uint32_t s_beg[kMaxBuckets], s_n[kMaxBuckets]; // staged run of each bucket
+    __shared__ ull s_g[kMaxBuckets];                          // where the run goes in ent_out
     if (meta->overflow) return;
-    const ull* __restrict__ offsets = meta->offsets[c];
-    ull* __restrict__ cursor = meta->cursor[c];
-    const uint32_t bucket0 = key_lo >> shift;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t n_steps = (blk_hi - blk_lo + kPartThreads - 1) / kPartThreads;
-
-    for (uint64_t step = blockIdx.x; step < n_steps; step += gridDim.x) {
-        if (tid < kMaxBuckets) s_cnt[tid] = 0;
-        __syncthreads();
-        const uint64_t gb = blk_lo + step * kPartThreads + tid;
-        uint32_t key[32];
-        uint32_t posw[16];  // rank inside the CTA's bucket run, two 16-bit values per word
-        uint32_t m = 0;
-        if (gb < blk_hi) {
-            const BlockWindows b = load_block(codes, valid, gb);
-            m = b.m;
-            if (m) {
-                if (WITH_RID) s_rid[tid] = __ldg(blk_read + gb);
-                const uint32_t r0 = rc16(b.w1), r1 = rc16(b.w0), r2 = rc16(b.pw);
-                if (FULL && m == 0xFFFFFFFFu) {  // interior block of a read, whole key space: no predicates at all
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const uint32_t kk = canonical15(kmer_ending_at<15>(b.pw, b.w0, b.w1, j), rc15_ending_at(r0, r1, r2, j));
-                        key[j] = kk;
-                        const uint32_t p = atomicAdd(&s_cnt[kk >> shift], 1u);
-                        if (j & 1) posw[j >> 1] |= p << 16; else posw[j >> 1] = p;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if ((j & 1) == 0) posw[j >> 1] = 0;
-                        key[j] = 0;
-                        if ((m >> j) & 1u) {
-                            const uint32_t kk = canonical15(kmer_ending_at<15>(b.pw, b.w0, b.w1, j), rc15_ending_at(r0, r1, r2, j));
-                            if (FULL || (kk >= key_lo && kk < key_hi)) {
-                                key[j] = kk;
-                                const uint32_t p = atomicAdd(&s_cnt[(kk >> shift) - bucket0], 1u);
-                                posw[j >> 1] |= p << (16 * (j & 1));
-                            } else {
-                                m &= ~(1u << j);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {  // exclusive scan of the bucket counts (nb <= 64: two per lane) + global reservation
-            const uint32_t c0 = (lane < nb) ? s_cnt[lane] : 0u;
-            const uint32_t c1 = (lane + 32 < nb) ? s_cnt[lane + 32] : 0u;
+    const uint32_t bucket0 = key_lo >> shift;
+    const uint32_t lo15 = 0x7FFFu, hi_mask = ((1u << (shift - 1)) - 1u) & ~lo15;
+    const uint32_t s_first = blockIdx.x * G, s_end = min(n_steps, s_first + G);
+    // lane l of warp 0 keeps the running offsets of buckets l and l+32 inside their regions
+    uint32_t run0 = 0, run1 = 0;
+    ull reg0 = 0, reg1 = 0;
+    if (warp == 0) {
+        if (lane < nb) { run0 = T.grp_off[(size_t)blockIdx.x * kMaxBuckets + lane]; reg0 = meta->offsets[c][lane]; }
+        if (lane + 32 < nb) { run1 = T.grp_off[(size_t)blockIdx.x * kMaxBuckets + lane + 32]; reg1 = meta->offsets[c][lane + 32]; }
+    }
+    for (uint32_t s = s_first; s < s_end; ++s) {
+        const uint64_t gb = blk_lo + (uint64_t)s * kPartThreads + tid;
+        BlockWindows b;
+        b.m = b.pw = b.w0 = b.w1 = 0;
+        if (gb < blk_hi) b = load_block(codes, valid, gb);
+        uint32_t rd = 0;
+        if (WITH_RID && b.m) rd = (__ldg(blk_read + gb) - T.rid0[step0 + s]) << (shift - 1);
+        if (warp == 0) {  // staging layout of the step from its (known) bucket counts
+            const uint16_t* cs = T.cnt + (size_t)(step0 + s) * kMaxBuckets;
+            const uint32_t c0 = (lane < nb) ? cs[lane] : 0u;
+            const uint32_t c1 = (lane + 32 < nb) ? cs[lane + 32] : 0u;
             uint32_t x0 = c0, x1 = c1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -197,92 +260,115 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
                 if (lane >= d) { x0 += y0; x1 += y1; }
             }
             const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
-            s_base[lane] = x0 - c0;
-            s_base[lane + 32] = tot0 + x1 - c1;
-            if (lane < nb && c0) s_gbase[lane] = offsets[lane] + atomicAdd(&cursor[lane], (ull)c0);
-            if (lane + 32 < nb && c1) s_gbase[lane + 32] = offsets[lane + 32] + atomicAdd(&cursor[lane + 32], (ull)c1);
+            s_cur[lane] = s_beg[lane] = x0 - c0;
+            s_cur[lane + 32] = s_beg[lane + 32] = tot0 + x1 - c1;
+            s_n[lane] = c0;
+            s_n[lane + 32] = c1;
+            s_g[lane] = reg0 + run0;
+            s_g[lane + 32] = reg1 + run1;
+            if (lane < nb) T.off[(size_t)lane * T.cap + step0 + s] = run0;
+            if (lane + 32 < nb) T.off[(size_t)(lane + 32) * T.cap + step0 + s] = run1;
+            run0 += c0;
+            run1 += c1;
         }
         __syncthreads();
-        if (m == 0xFFFFFFFFu) {
+        for_each_key<FULL>(b, key_lo, key_hi, [&](uint32_t kk) {
+            const uint32_t idx = atomicAdd(&s_cur[(kk >> shift) - bucket0], 1u);
+            s_ent[idx] = (kk & lo15) | ((kk >> 1) & hi_mask) | rd;
+        });
+        __syncthreads();
+        for (int bk = warp; bk < nb; bk += kPartThreads / 32) {  // each warp copies whole runs: contiguous both sides
+            const uint32_t n = s_n[bk];
+            if (!n) continue;
+            const uint32_t* src = s_ent + s_beg[bk];
+            uint32_t* dst = ent_out + s_g[bk];
+            for (uint32_t i = lane; i < n; i += 32) __stcs(dst + i, src[i]);
+        }
+        __syncthreads();
+    }
+    // terminal offsets (run lengths are differences of consecutive step_off entries)
+    if (warp == 0 && s_end == n_steps && s_first < s_end) {
+        if (lane < nb) T.off[(size_t)lane * T.cap + step0 + n_steps] = run0;
+        if (lane + 32 < nb) T.off[(size_t)(lane + 32) * T.cap + step0 + n_steps] = run1;
+    }
+}
+
+// list entry -> table index (bucket_base = first key of the bucket)
+__device__ __forceinline__ uint32_t entry_key(uint32_t e, uint32_t bucket_base, uint32_t hi_mask2) {
+    return bucket_base | (e & 0x7FFFu) | ((e << 1) & hi_mask2);
+}
+
+__global__ void __launch_bounds__(256)
+k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, uint32_t bucket_base,
+             uint32_t hi_mask2, uint32_t* __restrict__ table) {
+    if (meta->overflow) return;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint64_t n = meta->counts[c][bucket];
+        const uint32_t* __restrict__ ee = ents + meta->offsets[c][bucket];
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n; i += 4 * stride) {
+            const uint32_t e0 = __ldcs(ee + i), e1 = __ldcs(ee + i + stride), e2 = __ldcs(ee + i + 2 * stride),
+                           e3 = __ldcs(ee + i + 3 * stride);
+            atomicAdd(table + entry_key(e0, bucket_base, hi_mask2), 1u);
+            atomicAdd(table + entry_key(e1, bucket_base, hi_mask2), 1u);
+            atomicAdd(table + entry_key(e2, bucket_base, hi_mask2), 1u);
+            atomicAdd(table + entry_key(e3, bucket_base, hi_mask2), 1u);
+        }
+        for (; i < n; i += stride) atomicAdd(table + entry_key(__ldcs(ee + i), bucket_base, hi_mask2), 1u);
+    }
+}
+
+// entries of one bucket, one warp per run (the windows of one 8192-slot step): hist[read][bin(table[key])] += 1.
+// Four entries per lane are in flight (key stream, then four gathers) — the kernel is bound by the latency of the
+// dependent stream-load -> gather chain otherwise; equal (read, bin) entries of a warp share one RED.
+__global__ void __launch_bounds__(256)
+k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, ChunkList L,
+              StepTables T, uint32_t bucket_base, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
+              uint64_t magic, uint32_t B, uint32_t* __restrict__ hist) {
+    if (meta->overflow) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t* __restrict__ off_row = T.off + (size_t)bucket * T.cap;
+    for (int c = 0; c < n_chunks; ++c) {
+        if (!meta->counts[c][bucket]) continue;
+        const uint32_t* __restrict__ region = ents + meta->offsets[c][bucket];
+        const uint32_t s0 = L.step0[c], ns = L.nsteps[c];
+        for (uint32_t s = warp; s < ns; s += n_warps) {
+            const uint32_t beg = __ldg(off_row + s0 + s), end = __ldg(off_row + s0 + s + 1);
+            if (beg == end) continue;
+            const uint32_t rid0 = __ldg(T.rid0 + s0 + s);
+            for (uint32_t i0 = beg; i0 < end; i0 += 128) {
+                uint32_t e[4], cnt[4];
+                bool act[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t idx = s_base[(key[j] >> shift) - bucket0] + ((j & 1) ? (posw[j >> 1] >> 16) : (posw[j >> 1] & 0xFFFFu));
-                s_key[idx] = key[j];
-                if (WITH_RID) s_tid[idx] = (uint8_t)tid;
-            }
-        } else if (m) {
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t i = i0 + 32u * u + lane;
+                    act[u] = i < end;
+                    e[u] = act[u] ? __ldcs(region + i) : 0u;
+                }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if ((m >> j) & 1u) {
-                    const uint32_t idx = s_base[(key[j] >> shift) - bucket0] + ((posw[j >> 1] >> (16 * (j & 1))) & 0xFFFFu);
-                    s_key[idx] = key[j];
-                    if (WITH_RID) s_tid[idx] = (uint8_t)tid;
+                for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? table[entry_key(e[u], bucket_base, hi_mask2)] : 0u;  // L2-resident slice
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i0 + 32u * u >= end) break;  // warp-uniform
+                    const uint32_t cell = act[u] ? (e[u] >> (shift - 1)) * B + coverage_bin(cnt[u], S32, magic, B) : 0xFFFFFFFFu;
+                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cell);
+                    if (act[u] && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hist + (size_t)rid0 * B + cell, (uint32_t)__popc(peers));
                 }
             }
         }
-        __syncthreads();
-        for (int b = warp; b < nb; b += kPartThreads / 32) {  // each warp copies whole bucket runs: contiguous both sides
-            const uint32_t cnt = s_cnt[b];
-            if (!cnt) continue;
-            const uint32_t beg = s_base[b];
-            const ull g = s_gbase[b];
-            for (uint32_t i = lane; i < cnt; i += 32) {
-                __stcs(keys_out + g + i, s_key[beg + i]);
-                if (WITH_RID) __stcs(rids_out + g + i, s_rid[s_tid[beg + i]]);
-            }
-        }
-        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_count_keys(const uint32_t* __restrict__ keys, const PartMeta* __restrict__ meta, int bucket, int n_chunks,
-             uint32_t* __restrict__ table) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (int c = 0; c < n_chunks; ++c) {
-        const uint64_t n = meta->counts[c][bucket];
-        const uint32_t* __restrict__ kk = keys + meta->offsets[c][bucket];
-        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        for (; i + 3 * stride < n; i += 4 * stride) {
-            const uint32_t k0 = __ldcs(kk + i), k1 = __ldcs(kk + i + stride), k2 = __ldcs(kk + i + 2 * stride),
-                           k3 = __ldcs(kk + i + 3 * stride);
-            atomicAdd(table + k0, 1u);
-            atomicAdd(table + k1, 1u);
-            atomicAdd(table + k2, 1u);
-            atomicAdd(table + k3, 1u);
-        }
-        for (; i < n; i += stride) atomicAdd(table + __ldcs(kk + i), 1u);
-    }
-}
-
-// entries of one bucket: hist[read][bin(table[key])] += 1, sums[read] += 1, aggregated over runs of equal neighbours
-__global__ void __launch_bounds__(256)
-k_search_keys(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rids, const PartMeta* __restrict__ meta,
-              int bucket, int n_chunks, const uint32_t* __restrict__ table, uint32_t S32, uint64_t magic, uint32_t B,
-              uint32_t* __restrict__ hist, uint32_t* __restrict__ sums) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (int c = 0; c < n_chunks; ++c) {
-        const uint64_t n = meta->counts[c][bucket];
-        const uint64_t off = meta->offsets[c][bucket];
-        const uint32_t* __restrict__ kk = keys + off;
-        const uint32_t* __restrict__ rr = rids + off;
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += stride) {
-            const bool act = i < n;
-            const uint32_t key = act ? __ldcs(kk + i) : 0u;
-            const uint32_t rid = act ? __ldcs(rr + i) : 0xFFFFFFFFu;
-            const uint32_t cnt = act ? table[key] : 0u;  // slice resident in L2 (just counted, or warmed by earlier gathers)
-            const uint32_t bin = act ? coverage_bin(cnt, S32, magic, B) : 0xFFFFu;
-            // one RED per distinct (read, bin) and one per distinct read in the warp: consecutive list entries come from
-            // the same few reads and bins, and the L1/LSU sector rate (gather + REDs) is what bounds this kernel
-            const uint32_t m_r = __match_any_sync(0xFFFFFFFFu, rid);
-            const uint32_t m_g = m_r & __match_any_sync(0xFFFFFFFFu, bin);
-            if (act) {
-                if ((uint32_t)__ffs(m_g) - 1u == lane) atomicAdd(hist + (size_t)rid * B + bin, (uint32_t)__popc(m_g));
-                if ((uint32_t)__ffs(m_r) - 1u == lane) atomicAdd(sums + rid, (uint32_t)__popc(m_r));
-            }
-        }
-    }
+// sums[r] = number of windows of read r that were bucketed so far = sum of its histogram row
+__global__ void __launch_bounds__(256) k_row_sums(const uint32_t* __restrict__ hist, uint32_t* __restrict__ sums, uint64_t n_reads, uint32_t B) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint32_t* row = hist + r * B;
+    uint32_t s = 0;
+    for (uint32_t i = 0; i < B; ++i) s += row[i];
+    sums[r] = s;
 }
 
 int sms() {
@@ -292,6 +378,16 @@ int sms() {
 }
 
 }  // namespace
+
+extern "C" uint64_t lrb_partition_step_capacity(uint64_t n_blocks, int max_chunks) {
+    if (max_chunks < 1) max_chunks = 1;
+    // every chunk owns ceil(blocks/256) steps + one terminal slot; adds larger than 2^26 blocks are split
+    return n_blocks / kPartThreads + 2ull * (uint64_t)max_chunks + 2ull * (n_blocks / kMaxChunkBlocks + 1) + 2;
+}
+
+extern "C" uint64_t lrb_partition_steps_words(uint64_t step_capacity) {
+    return 2ull * kMaxGroups * kMaxBuckets + step_capacity * (1 + kMaxBuckets / 2 + kMaxBuckets);
+}
 
 extern "C" int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_read, void* stream) {
     if (!dev || !blk_read) return lrb_set_error(LRB_EINVAL, "lrb_dev_fill_blk_read: null argument");
@@ -305,11 +401,10 @@ extern "C" int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_re
 // ---- host side: begin, add chunk(s) of the stream, then count and/or search bucket by bucket -------------------
 extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint32_t key_lo, uint32_t key_hi,
                                        int log2_bucket_keys, void* stream) {
-    if (!part || !part->keys || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_begin: null argument");
-    if (with_rids && !part->rids) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_begin: read ids need part->rids");
+    if (!part || !part->keys || !part->small || !part->steps) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_begin: null argument");
     if (key_hi > kTableEntries) key_hi = kTableEntries;
     const int shift = log2_bucket_keys;
-    if (shift < 20 || shift > 30) return lrb_set_error(LRB_EINVAL, "log2_bucket_keys must be in [20, 30]");
+    if (shift < 20 || shift > 25) return lrb_set_error(LRB_EINVAL, "log2_bucket_keys must be in [20, 25]");
     const uint32_t bsz = 1u << shift;
     if (key_lo >= key_hi || (key_lo & (bsz - 1)) || (key_hi & (bsz - 1)))
         return lrb_set_error(LRB_EINVAL, "key range must be non-empty and aligned to the bucket size 2^%d", shift);
@@ -321,39 +416,61 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
     part->key_hi = key_hi;
     part->has_rids = with_rids ? 1 : 0;
     part->n_chunks = 0;
+    part->steps_used = 0;
+    part->n_reads = 0;
     LRB_CUDA(cudaMemsetAsync(part->small, 0, sizeof(PartMeta), (cudaStream_t)stream));
+    return LRB_OK;
+}
+
+static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64_t blk_lo, uint64_t blk_hi, lrb_partition* part,
+                     cudaStream_t st) {
+    if (part->n_chunks >= kMaxChunks) return lrb_set_error(LRB_EINVAL, "too many chunks in one partition (max %d)", kMaxChunks);
+    const uint64_t nblk = blk_hi - blk_lo;
+    const uint32_t n_steps = (uint32_t)((nblk + kPartThreads - 1) / kPartThreads);
+    if (part->steps_used + n_steps + 1 > part->step_capacity)
+        return lrb_set_error(LRB_ENOMEM, "partition step tables too small: %llu steps needed, %llu available (lrb_partition_step_capacity)",
+                             (ull)(part->steps_used + n_steps + 1), (ull)part->step_capacity);
+    const int c = part->n_chunks++;
+    const uint32_t step0 = (uint32_t)part->steps_used;
+    part->chunk_step0[c] = step0;
+    part->chunk_nsteps[c] = n_steps;
+    part->steps_used += n_steps + 1;
+    PartMeta* meta = reinterpret_cast<PartMeta*>(part->small);
+    const StepTables T = step_tables(part->steps, part->step_capacity);
+    const int nb = part->n_buckets, shift = part->shift;
+    // groups of consecutive steps, one CTA each in both passes; enough of them to fill the machine several times
+    const uint32_t want_groups = (uint32_t)std::min<uint64_t>((uint64_t)sms() * 32, kMaxGroups);
+    const uint32_t G = std::max<uint32_t>(1, (n_steps + want_groups - 1) / want_groups);
+    const uint32_t n_groups = (n_steps + G - 1) / G;
+    const bool full = part->key_lo == 0 && part->key_hi >= kTableEntries;
+    const uint32_t* br = part->has_rids ? blk_read : nullptr;
+    if (full)
+        k_step_hist<true><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T);
+    else
+        k_step_hist<false><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T);
+    k_group_scan<<<nb, 256, 0, st>>>(T, n_groups, meta, c);
+    k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity);
+#define LRB_LAUNCH_PART(RID, FULLK)                                                                                                   \
+    k_partition<RID, FULLK><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, \
+                                                               shift, nb, n_steps, G, step0, T, meta, c, part->keys)
+    if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
+    else { if (full) LRB_LAUNCH_PART(false, true); else LRB_LAUNCH_PART(false, false); }
+#undef LRB_LAUNCH_PART
+    LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
 
 extern "C" int lrb_dev_partition_add(const lrb_reads_view* dev, const uint32_t* blk_read, uint64_t blk_lo, uint64_t blk_hi,
                                      lrb_partition* part, void* stream) {
-    if (!dev || !part || !part->keys || !part->small) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_add: null argument");
+    if (!dev || !part || !part->keys || !part->small || !part->steps) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_add: null argument");
     if (part->has_rids && !blk_read) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_add: read ids need blk_read");
     if (blk_hi > dev->n_blocks) blk_hi = dev->n_blocks;
     if (blk_lo >= blk_hi) return LRB_OK;
-    if (part->n_chunks >= kMaxChunks) return lrb_set_error(LRB_EINVAL, "too many chunks in one partition (max %d)", kMaxChunks);
-    const int c = part->n_chunks++;
-    cudaStream_t st = (cudaStream_t)stream;
-    PartMeta* meta = reinterpret_cast<PartMeta*>(part->small);
-    const uint64_t nblk = blk_hi - blk_lo;
-    const int nsm = sms();
-    const int nb = part->n_buckets, shift = part->shift;
-    {
-        const uint64_t want = (nblk + 255) / 256;
-        const unsigned grid = (unsigned)std::min<uint64_t>(want, (uint64_t)nsm * 8);
-        k_bucket_hist<<<grid, 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, &meta->counts[c][0]);
-        k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity);
+    part->n_reads = std::max<uint64_t>(part->n_reads, dev->n_reads);
+    for (uint64_t lo = blk_lo; lo < blk_hi; lo += kMaxChunkBlocks) {
+        const int rc = add_chunk(dev, blk_read, lo, std::min(blk_hi, lo + kMaxChunkBlocks), part, (cudaStream_t)stream);
+        if (rc) return rc;
     }
-    const uint64_t n_steps = (nblk + kPartThreads - 1) / kPartThreads;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_steps, (uint64_t)nsm * 24);
-    const bool full = part->key_lo == 0 && part->key_hi >= kTableEntries;
-#define LRB_LAUNCH_PART(RID, FULLK)                                                                                              \
-    k_partition<RID, FULLK><<<grid, kPartThreads, 0, st>>>(dev->codes, dev->valid, blk_read, blk_lo, blk_hi, part->key_lo, part->key_hi, \
-                                                           shift, nb, meta, c, part->keys, part->rids)
-    if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
-    else { if (full) LRB_LAUNCH_PART(false, true); else LRB_LAUNCH_PART(false, false); }
-#undef LRB_LAUNCH_PART
-    LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
 
@@ -395,11 +512,27 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const uint32_t S32 = bin_size > 0xFFFFFFFFl ? 0xFFFFFFFFu : (uint32_t)(bin_size > 0 ? bin_size : 1);
     const uint64_t magic = coverage_magic(S32);
     const PartMeta* meta = reinterpret_cast<const PartMeta*>(part->small);
-    const unsigned grid = (unsigned)sms() * 8;
-    for (int b = 0; b < part->n_buckets; ++b) {
-        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, table);
-        if (do_search) k_search_keys<<<grid, 256, 0, st>>>(part->keys, part->rids, meta, b, part->n_chunks, table, S32, magic, (uint32_t)bins, hist, sums);
+    const StepTables T = step_tables(part->steps, part->step_capacity);
+    ChunkList L;
+    uint32_t max_steps = 0;
+    for (int c = 0; c < kMaxChunks; ++c) {
+        L.step0[c] = c < part->n_chunks ? part->chunk_step0[c] : 0u;
+        L.nsteps[c] = c < part->n_chunks ? part->chunk_nsteps[c] : 0u;
+        max_steps = std::max(max_steps, L.nsteps[c]);
     }
+    const int shift = part->shift;
+    const uint32_t hi_mask2 = ((1u << shift) - 1u) & ~0xFFFFu;
+    const unsigned grid = (unsigned)sms() * 8;
+    const unsigned sgrid = (unsigned)std::min<uint64_t>(grid, (max_steps + 7) / 8 + 1);  // 8 warps (runs) per CTA
+    for (int b = 0; b < part->n_buckets; ++b) {
+        const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
+        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table);
+        if (do_search)
+            k_search_keys<<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic,
+                                                 (uint32_t)bins, hist);
+    }
+    if (do_search && part->n_reads)
+        k_row_sums<<<(unsigned)((part->n_reads + 255) / 256), 256, 0, st>>>(hist, sums, part->n_reads, (uint32_t)bins);
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

@@ -235,8 +235,9 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     ms_step, res, phases = timed(best, args.steps)
     clocks = sampler.stop()
     nbk = eng.ws.part.n_buckets
-    # composition + bucket_hist + partition + per-bucket count and search kernels (+ mirror; plan B partitions twice)
-    launches = {"keyshard_rs": 3 + 2 * nbk, "keyshard_ag": 6 + 2 * nbk, "readshard_ar": 4 + 2 * nbk}[best] * args.steps
+    # composition + 4 partition kernels (step hist, two scans, partition) + per-bucket count and search kernels + row sums
+    # (+ mirror; plan B partitions twice)
+    launches = {"keyshard_rs": 6 + 2 * nbk, "keyshard_ag": 11 + 2 * nbk, "readshard_ar": 7 + 2 * nbk}[best] * args.steps
 
     # e2e: every step also moves this rank's inputs host->device and its result rows device->host
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

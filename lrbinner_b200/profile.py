@@ -17,6 +17,7 @@ from . import _lib
 from ._lib import ReadsView, check, lib
 
 COMP_WIDTH = {3: 32, 4: 136, 5: 512}
+LRB_MAX_CHUNKS = 64
 
 
 def _ptr(a):
@@ -80,6 +81,20 @@ class PackedReads:
     read_blk = property(lambda self: self._arr(self.view.read_blk, self.n_reads + 1))
     tile_read = property(lambda self: self._arr(self.view.tile_read, self.n_tiles))
     tile_blk = property(lambda self: self._arr(self.view.tile_blk, self.n_tiles))
+
+    def index_valid(self, threads=8):
+        """(Re)build the validity-exception list from the current `valid` words; returns its length."""
+        n = C.c_uint64(0)
+        check(lib.lrb_reads_index_valid(self._h, int(threads), C.byref(n)))
+        return int(n.value)
+
+    def exceptions(self):
+        """(blocks, words) of the validity-exception list (copies; empty when none was built)."""
+        blk, word, n = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        check(lib.lrb_reads_exceptions(self._h, C.byref(blk), C.byref(word), C.byref(n)))
+        if not n.value:
+            return np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint32)
+        return (np.array(self._arr(blk, int(n.value)), copy=True), np.array(self._arr(word, int(n.value)), copy=True))
 
     def unpack(self, i):
         n = int(self.read_len[i])
@@ -237,6 +252,13 @@ def dev_count(dr, table, blk_lo=0, blk_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTR
                             key_lo, min(key_hi, _lib.TABLE_ENTRIES), _stream()))
 
 
+def dev_fill_valid(dr, exc_blk=None, exc_word=None):
+    """Rebuild dr.valid on the device from the read lengths + the exception list (torch int32 tensors or None)."""
+    n = 0 if exc_blk is None else int(exc_blk.numel())
+    check(lib.lrb_dev_fill_valid(C.byref(dr.view), C.c_void_p(exc_blk.data_ptr()) if n else None,
+                                 C.c_void_p(exc_word.data_ptr()) if n else None, n, _stream()))
+
+
 def dev_mirror(table):
     check(lib.lrb_dev_mirror(C.c_void_p(table.data_ptr()), _stream()))
 
@@ -248,20 +270,21 @@ def dev_search(dr, table, bin_size, bins, hist, sums, tile_lo=0, tile_hi=None, k
 
 
 class PartitionWorkspace:
-    """Scratch of the L2-resident table passes: (key, read) lists for up to `capacity` windows, the per-block
-    read index, and the lrb_partition descriptor the C ABI fills."""
+    """Scratch of the L2-resident table passes: 4-byte list entries for up to `capacity` windows, the per-step
+    tables, the per-block read index, and the lrb_partition descriptor the C ABI fills."""
 
-    def __init__(self, dr, capacity=None, with_rids=True):
+    def __init__(self, dr, capacity=None, max_chunks=LRB_MAX_CHUNKS):
         torch = dr.torch
         self.dr = dr
         self.capacity = int(capacity if capacity is not None else max(dr.n_blocks * 32, 1))
         self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
-        self.rids = torch.empty(self.capacity, dtype=torch.int32, device=dr.device) if with_rids else None
         self.small = torch.zeros(_lib.PART_SMALL_U64, dtype=torch.int64, device=dr.device)
+        self.step_capacity = int(lib.lrb_partition_step_capacity(dr.n_blocks, max_chunks))
+        self.steps = torch.empty(int(lib.lrb_partition_steps_words(self.step_capacity)), dtype=torch.int32, device=dr.device)
         self.blk_read = torch.empty(max(dr.n_blocks, 1), dtype=torch.int32, device=dr.device)
         check(lib.lrb_dev_fill_blk_read(C.byref(dr.view), C.c_void_p(self.blk_read.data_ptr()), _stream()))
-        self.part = _lib.Partition(keys=self.keys.data_ptr(), rids=self.rids.data_ptr() if with_rids else None,
-                                   small=self.small.data_ptr(), capacity=self.capacity)
+        self.part = _lib.Partition(keys=self.keys.data_ptr(), small=self.small.data_ptr(), steps=self.steps.data_ptr(),
+                                   capacity=self.capacity, step_capacity=self.step_capacity)
 
     def begin(self, with_rids=True, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24):
         check(lib.lrb_dev_partition_begin(C.byref(self.part), 1 if with_rids else 0, key_lo, min(key_hi, _lib.TABLE_ENTRIES),
@@ -279,12 +302,11 @@ class PartitionWorkspace:
             rc = lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream())
             if rc == _lib.LRB_ENOMEM:
                 torch = self.dr.torch
-                self.keys = self.rids = None
+                self.keys = None
                 torch.cuda.empty_cache()
                 self.capacity = int(needed.value) + int(needed.value) // 64 + 1024
                 self.keys = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
-                self.rids = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
-                self.part.keys, self.part.rids, self.part.capacity = self.keys.data_ptr(), self.rids.data_ptr(), self.capacity
+                self.part.keys, self.part.capacity = self.keys.data_ptr(), self.capacity
                 self.begin(with_rids, key_lo, key_hi, log2_bucket_keys)
                 self.add(blk_lo, blk_hi)
                 rc = lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream())

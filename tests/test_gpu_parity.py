@@ -211,6 +211,29 @@ def test_device_synth_and_pack_match_host():
     assert np.array_equal(d2.valid.cpu().numpy().view(np.uint32)[:host.n_blocks + 1], host.valid)
 
 
+def test_device_validity_rebuild_from_exceptions(ctx):
+    """lrb_dev_fill_valid (read lengths + sparse exceptions) reproduces the host bitmap; the host path that ships
+    exceptions instead of the bitmap gives the same profiles as the one that ships the bitmap."""
+    from lrbinner_b200.profile import dev_fill_valid
+    spec = SynthSpec(2000, seed=13, n_rate=2e-3, lowercase_frac=0.01, edge_lengths=True, scale=0.02)
+    pr = spec.host_packed(threads=4)
+    blk, word = pr.exceptions()
+    assert 0 < len(blk) < pr.n_blocks // 16
+    dr = DeviceReads(pr, DEV)
+    dr.valid.fill_(0x5A5A5A5A)
+    dev_fill_valid(dr, torch.from_numpy(blk.view(np.int32)).to(DEV), torch.from_numpy(word.view(np.int32)).to(DEV))
+    assert np.array_equal(dr.valid.cpu().numpy().view(np.uint32)[:pr.n_blocks + 1], pr.valid)
+    res_exc = ctx.profile(pr, k=4, bin_size=32, bins=10, want_table=False)
+    os.environ["LRB_SHIP_VALID"] = "1"
+    try:
+        res_map = ctx.profile(pr, k=4, bin_size=32, bins=10, want_table=False)
+    finally:
+        del os.environ["LRB_SHIP_VALID"]
+    for key in ("comp", "hist", "sums"):
+        assert np.array_equal(res_exc[key], res_map[key]), key
+    assert int(res_exc["sums"].sum()) > 0
+
+
 def test_device_text_epilogue_matches_host_writer(tmp_path, ctx):
     spec = SynthSpec(700, seed=4, n_rate=1e-3, edge_lengths=True, scale=0.02)
     pr = spec.host_packed()
@@ -284,7 +307,7 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     ws = PartitionWorkspace(dr)
     blk = np.array(pr.read_blk)
     assert np.array_equal(ws.blk_read.cpu().numpy().view(np.uint32)[:pr.n_blocks], np.repeat(np.arange(n, dtype=np.uint32), np.diff(blk)))
-    for shift in (25, 24, 27):
+    for shift in (25, 24):
         table_p, hist_p, sums_p = z(2 ** 30), z(n, bc), z(n)
         dev_table15_partitioned(dr, ws, table_p, True, bs, bc, hist_p, sums_p, log2_bucket_keys=shift)      # fused
         assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d), shift
@@ -306,6 +329,11 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
         for blo, bhi in ((0, int(blk[n // 2])), (int(blk[n // 2]), nb)):
             dev_table15_partitioned(dr, ws, table_p, False, bs, bc, hist_p, sums_p, blk_lo=blo, blk_hi=bhi, key_lo=klo, key_hi=khi)
     assert torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
+    # small buckets on a narrow key range (what an 8-GPU key shard looks like), then the rest of the key space
+    table_p, hist_p, sums_p = z(2 ** 30), z(n, bc), z(n)
+    for klo, khi, shift in ((0, 2 ** 26, 20), (2 ** 26, 2 ** 27, 21), (2 ** 27, 2 ** 30, 24)):
+        dev_table15_partitioned(dr, ws, table_p, True, bs, bc, hist_p, sums_p, key_lo=klo, key_hi=khi, log2_bucket_keys=shift)
+    assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
     # workspace too small is an error, not a truncation
     small = PartitionWorkspace(dr, capacity=1000)
     t_small = z(2 ** 30)

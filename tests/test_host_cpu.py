@@ -152,6 +152,43 @@ def test_from_sequences_and_lengths_layout():
     assert np.array_equal(pl.tile_read, pr.tile_read) and not pl.codes.any()
 
 
+def _default_valid(pr):
+    blk, ln = np.array(pr.read_blk, dtype=np.int64), np.array(pr.read_len, dtype=np.int64)
+    want = np.zeros(pr.n_blocks + 1, dtype=np.uint32)
+    for r in range(pr.n_reads):
+        for b in range(blk[r], blk[r + 1]):
+            n_in = min(32, max(0, ln[r] - 32 * (b - blk[r])))
+            want[b] = 0xFFFFFFFF if n_in == 32 else (1 << n_in) - 1
+    return want
+
+
+def test_validity_exceptions_index():
+    """The exception list (what lrb_profile_host ships instead of the bitmap) + the length-implied words == valid."""
+    rng = np.random.default_rng(5)
+    lens = [0, 1, 31, 32, 33, 64, 700, 8193, 3000, 0, 5, 2500]
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [bytearray(rng.choice(alphabet, size=n).tobytes()) for n in lens]
+    seqs[6][10] = ord("N"); seqs[6][699] = ord("a"); seqs[7][8192] = ord("n"); seqs[8][0] = ord("R")
+    seqs[11] = bytearray(bytes(seqs[11]).lower())
+    for threads in (1, 4):
+        pr = PackedReads.from_sequences([bytes(s) for s in seqs], threads=threads)
+        blk, word = pr.exceptions()
+        want = _default_valid(pr)
+        assert np.all(np.diff(blk.astype(np.int64)) > 0)
+        assert np.all(want[blk] != word)
+        want[blk] = word
+        assert np.array_equal(want, pr.valid)
+        assert len(blk) == 1 + 1 + 1 + 1 + (2500 // 32 + 1)     # N, a, n, R and every block of the lowercase read
+    # a hand-filled layout has no list until it is indexed
+    pl = PackedReads.from_lengths(np.array(lens, dtype=np.uint32))
+    assert len(pl.exceptions()[0]) == 0
+    pl.codes[:] = pr.codes
+    pl.valid[:] = pr.valid
+    assert pl.index_valid(threads=3) == len(blk)
+    b2, w2 = pl.exceptions()
+    assert np.array_equal(b2, blk) and np.array_equal(w2, word)
+
+
 # ---- exact "%f" ------------------------------------------------------------------------------------
 
 def test_fixed6_matches_printf():
