@@ -85,6 +85,7 @@ __host__ __device__ inline StepTables step_tables(uint32_t* steps, uint64_t cap)
 struct ChunkList {  // by-value kernel argument of the apply kernels
     uint32_t step0[kMaxChunks];
     uint32_t nsteps[kMaxChunks];
+    uint32_t task0[kMaxChunks + 1];  // first search task of each chunk (k_search_keys)
 };
 
 __global__ void __launch_bounds__(256) k_fill_blk_read(lrb_reads_view R, uint32_t* __restrict__ blk_read) {
@@ -221,15 +222,20 @@ __global__ void k_chunk_scan(PartMeta* __restrict__ m, int c, int nb, ull capaci
 }
 
 // ---- pass 2: entries -> bucket regions ---------------------------------------------------------------------
+// Per step: (prelude, warp 0) staging layout from the step's known bucket counts; (rank + place) every window takes
+// the next staging slot of its bucket with one shared-memory atomic and drops its entry there; (copy-out) each warp
+// copies whole runs, contiguous on both sides.  The next step's block and prelude are fetched while the current one
+// is copied out; two barriers per step.  The kernel is bound by shared-memory wavefronts (the scattered staging
+// store and the ranking atomic), so nothing else is staged.
 template <bool WITH_RID, bool FULL>
 __global__ void __launch_bounds__(kPartThreads)
 k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
             uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb, uint32_t n_steps, uint32_t G,
             uint32_t step0, StepTables T, const PartMeta* __restrict__ meta, int c, uint32_t* __restrict__ ent_out) {
-    __shared__ uint32_t s_ent[kStepSlots];                    // staged entries, grouped by bucket
-    __shared__ uint32_t s_cur[kMaxBuckets];                   // staging cursor of each bucket
-    __shared__ uint32_t s_beg[kMaxBuckets], s_n[kMaxBuckets]; // staged run of each bucket
-    __shared__ ull s_g[kMaxBuckets];                          // where the run goes in ent_out
+    __shared__ uint32_t s_ent[kStepSlots];                          // staged entries, grouped by bucket
+    __shared__ uint32_t s_cur[2][kMaxBuckets];                      // staging cursor of each bucket
+    __shared__ uint32_t s_beg[2][kMaxBuckets], s_n[2][kMaxBuckets]; // staged run of each bucket
+    __shared__ uint32_t* s_dst[2][kMaxBuckets];                     // where the run goes in ent_out
     if (meta->overflow) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bucket0 = key_lo >> shift;
@@ -242,46 +248,69 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
         if (lane < nb) { run0 = T.grp_off[(size_t)blockIdx.x * kMaxBuckets + lane]; reg0 = meta->offsets[c][lane]; }
         if (lane + 32 < nb) { run1 = T.grp_off[(size_t)blockIdx.x * kMaxBuckets + lane + 32]; reg1 = meta->offsets[c][lane + 32]; }
     }
-    for (uint32_t s = s_first; s < s_end; ++s) {
-        const uint64_t gb = blk_lo + (uint64_t)s * kPartThreads + tid;
-        BlockWindows b;
-        b.m = b.pw = b.w0 = b.w1 = 0;
-        if (gb < blk_hi) b = load_block(codes, valid, gb);
-        uint32_t rd = 0;
-        if (WITH_RID && b.m) rd = (__ldg(blk_read + gb) - T.rid0[step0 + s]) << (shift - 1);
-        if (warp == 0) {  // staging layout of the step from its (known) bucket counts
-            const uint16_t* cs = T.cnt + (size_t)(step0 + s) * kMaxBuckets;
-            const uint32_t c0 = (lane < nb) ? cs[lane] : 0u;
-            const uint32_t c1 = (lane + 32 < nb) ? cs[lane + 32] : 0u;
-            uint32_t x0 = c0, x1 = c1;
+    auto prelude = [&](uint32_t s, int buf) {  // warp 0 only
+        const uint16_t* cs = T.cnt + (size_t)(step0 + s) * kMaxBuckets;
+        const uint32_t c0 = (lane < nb) ? cs[lane] : 0u;
+        const uint32_t c1 = (lane + 32 < nb) ? cs[lane + 32] : 0u;
+        uint32_t x0 = c0, x1 = c1;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d);
-                if (lane >= d) { x0 += y0; x1 += y1; }
-            }
-            const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
-            s_cur[lane] = s_beg[lane] = x0 - c0;
-            s_cur[lane + 32] = s_beg[lane + 32] = tot0 + x1 - c1;
-            s_n[lane] = c0;
-            s_n[lane + 32] = c1;
-            s_g[lane] = reg0 + run0;
-            s_g[lane + 32] = reg1 + run1;
-            if (lane < nb) T.off[(size_t)lane * T.cap + step0 + s] = run0;
-            if (lane + 32 < nb) T.off[(size_t)(lane + 32) * T.cap + step0 + s] = run1;
-            run0 += c0;
-            run1 += c1;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d);
+            if (lane >= d) { x0 += y0; x1 += y1; }
         }
-        __syncthreads();
+        const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
+        const uint32_t e0 = x0 - c0, e1 = tot0 + x1 - c1;  // exclusive staging offsets
+        s_cur[buf][lane] = s_beg[buf][lane] = e0;
+        s_cur[buf][lane + 32] = s_beg[buf][lane + 32] = e1;
+        s_n[buf][lane] = c0;
+        s_n[buf][lane + 32] = c1;
+        s_dst[buf][lane] = ent_out + (reg0 + run0);
+        s_dst[buf][lane + 32] = ent_out + (reg1 + run1);
+        if (lane < nb) T.off[(size_t)lane * T.cap + step0 + s] = run0;
+        if (lane + 32 < nb) T.off[(size_t)(lane + 32) * T.cap + step0 + s] = run1;
+        run0 += c0;
+        run1 += c1;
+    };
+    // all loads of a block are issued back to back (no load depends on another), so a prefetch never stalls
+    auto fetch = [&](uint32_t s, uint32_t& v, uint32_t& pv, BlockWindows& b, uint32_t& rd) {
+        const uint64_t gb = blk_lo + (uint64_t)s * kPartThreads + tid;
+        v = pv = b.pw = b.w0 = b.w1 = rd = 0;
+        if (gb < blk_hi) {
+            v = __ldg(valid + gb);
+            pv = gb ? __ldg(valid + gb - 1) : 0u;
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(codes) + gb);
+            b.w0 = w.x;
+            b.w1 = w.y;
+            b.pw = gb ? __ldg(codes + 2 * gb - 1) : 0u;
+            if (WITH_RID) rd = __ldg(blk_read + gb) - __ldg(T.rid0 + step0 + s);
+        }
+    };
+    BlockWindows b;
+    uint32_t v, pv, rd;
+    if (s_first < s_end) {
+        fetch(s_first, v, pv, b, rd);
+        if (warp == 0) prelude(s_first, 0);
+    }
+    __syncthreads();
+    for (uint32_t s = s_first; s < s_end; ++s) {
+        const int buf = (int)((s - s_first) & 1u);
+        uint32_t* cur = s_cur[buf];
+        b.m = window15_mask(pv, v);
+        const uint32_t rds = rd << (shift - 1);
         for_each_key<FULL>(b, key_lo, key_hi, [&](uint32_t kk) {
-            const uint32_t idx = atomicAdd(&s_cur[(kk >> shift) - bucket0], 1u);
-            s_ent[idx] = (kk & lo15) | ((kk >> 1) & hi_mask) | rd;
+            const uint32_t idx = atomicAdd(&cur[(kk >> shift) - bucket0], 1u);
+            s_ent[idx] = (kk & lo15) | ((kk >> 1) & hi_mask) | rds;
         });
         __syncthreads();
+        if (s + 1 < s_end) {  // next step's inputs travel while this one is copied out
+            fetch(s + 1, v, pv, b, rd);
+            if (warp == 0) prelude(s + 1, buf ^ 1);
+        }
         for (int bk = warp; bk < nb; bk += kPartThreads / 32) {  // each warp copies whole runs: contiguous both sides
-            const uint32_t n = s_n[bk];
-            if (!n) continue;
-            const uint32_t* src = s_ent + s_beg[bk];
-            uint32_t* dst = ent_out + s_g[bk];
+            const uint32_t n = s_n[buf][bk];
+            const uint32_t* src = s_ent + s_beg[buf][bk];
+            uint32_t* dst = s_dst[buf][bk];
+#pragma unroll 2
             for (uint32_t i = lane; i < n; i += 32) __stcs(dst + i, src[i]);
         }
         __syncthreads();
@@ -319,43 +348,61 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
     }
 }
 
-// entries of one bucket, one warp per run (the windows of one 8192-slot step): hist[read][bin(table[key])] += 1.
-// Four entries per lane are in flight (key stream, then four gathers) — the kernel is bound by the latency of the
-// dependent stream-load -> gather chain otherwise; equal (read, bin) entries of a warp share one RED.
+// entries of one bucket: hist[read][bin(table[key])] += 1.  A warp task is kTaskRuns consecutive runs of one chunk —
+// one contiguous span of the bucket's region — streamed 128 entries per step (four gathers in flight per lane; the
+// kernel is bound by the latency of the dependent stream-load -> gather chain otherwise).  The run boundaries and
+// first-read indices of the span sit in shared memory; each lane walks them monotonically to recover the read of
+// its entries.  Equal (read, bin) entries of a warp share one RED.  Tasks are numbered across all chunks
+// (L.task0 = prefix of tasks per chunk) so small chunks still fill the machine.
+constexpr uint32_t kTaskRuns = 16;
+
 __global__ void __launch_bounds__(256)
 k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, ChunkList L,
               StepTables T, uint32_t bucket_base, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
               uint64_t magic, uint32_t B, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_bnd[8][kTaskRuns + 1];  // per warp: start of each run of the span, [kTaskRuns] = end of the span
+    __shared__ uint32_t s_r0[8][kTaskRuns];       // per warp: read index of the first block of each run's step
     if (meta->overflow) return;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t* __restrict__ off_row = T.off + (size_t)bucket * T.cap;
-    for (int c = 0; c < n_chunks; ++c) {
-        if (!meta->counts[c][bucket]) continue;
-        const uint32_t* __restrict__ region = ents + meta->offsets[c][bucket];
+    uint32_t* bnd = s_bnd[wl];
+    uint32_t* r0 = s_r0[wl];
+    const uint32_t n_tasks = L.task0[n_chunks];
+    int c = 0;
+    for (uint32_t task = warp; task < n_tasks; task += n_warps) {
+        while (task >= L.task0[c + 1]) ++c;  // tasks ascend: the chunk index only moves forward
         const uint32_t s0 = L.step0[c], ns = L.nsteps[c];
-        for (uint32_t s = warp; s < ns; s += n_warps) {
-            const uint32_t beg = __ldg(off_row + s0 + s), end = __ldg(off_row + s0 + s + 1);
-            if (beg == end) continue;
-            const uint32_t rid0 = __ldg(T.rid0 + s0 + s);
-            for (uint32_t i0 = beg; i0 < end; i0 += 128) {
-                uint32_t e[4], cnt[4];
-                bool act[4];
+        const uint32_t sb = (task - L.task0[c]) * kTaskRuns;
+        const uint32_t* __restrict__ region = ents + meta->offsets[c][bucket];
+        __syncwarp();
+        if (lane <= kTaskRuns) bnd[lane] = __ldg(off_row + s0 + min(sb + lane, ns));  // off_row[s0 + ns] is the terminal offset
+        if (lane < kTaskRuns) r0[lane] = __ldg(T.rid0 + s0 + min(sb + lane, ns - 1u));
+        __syncwarp();
+        const uint32_t span_beg = bnd[0], span_end = bnd[kTaskRuns], rbase = r0[0];
+        uint32_t cur = 0;  // run of this lane's current entry
+        for (uint32_t i0 = span_beg; i0 < span_end; i0 += 128) {
+            uint32_t e[4], cnt[4];
+            bool act[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t i = i0 + 32u * u + lane;
-                    act[u] = i < end;
-                    e[u] = act[u] ? __ldcs(region + i) : 0u;
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t i = i0 + 32u * u + lane;
+                act[u] = i < span_end;
+                e[u] = act[u] ? __ldcs(region + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? table[entry_key(e[u], bucket_base, hi_mask2)] : 0u;  // L2-resident slice
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + 32u * u >= span_end) break;  // warp-uniform
+                const uint32_t i = i0 + 32u * u + lane;
+                uint32_t cell = 0xFFFFFFFFu;
+                if (act[u]) {
+                    while (i >= bnd[cur + 1]) ++cur;   // runs may be empty; cur < kTaskRuns because i < bnd[kTaskRuns]
+                    cell = (r0[cur] - rbase + (e[u] >> (shift - 1))) * B + coverage_bin(cnt[u], S32, magic, B);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? table[entry_key(e[u], bucket_base, hi_mask2)] : 0u;  // L2-resident slice
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (i0 + 32u * u >= end) break;  // warp-uniform
-                    const uint32_t cell = act[u] ? (e[u] >> (shift - 1)) * B + coverage_bin(cnt[u], S32, magic, B) : 0xFFFFFFFFu;
-                    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cell);
-                    if (act[u] && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hist + (size_t)rid0 * B + cell, (uint32_t)__popc(peers));
-                }
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cell);
+                if (act[u] && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hist + (size_t)rbase * B + cell, (uint32_t)__popc(peers));
             }
         }
     }
@@ -514,16 +561,17 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const PartMeta* meta = reinterpret_cast<const PartMeta*>(part->small);
     const StepTables T = step_tables(part->steps, part->step_capacity);
     ChunkList L;
-    uint32_t max_steps = 0;
+    L.task0[0] = 0;
     for (int c = 0; c < kMaxChunks; ++c) {
         L.step0[c] = c < part->n_chunks ? part->chunk_step0[c] : 0u;
         L.nsteps[c] = c < part->n_chunks ? part->chunk_nsteps[c] : 0u;
-        max_steps = std::max(max_steps, L.nsteps[c]);
+        L.task0[c + 1] = L.task0[c] + (L.nsteps[c] + kTaskRuns - 1) / kTaskRuns;
     }
+    const uint32_t n_tasks = L.task0[part->n_chunks];
     const int shift = part->shift;
     const uint32_t hi_mask2 = ((1u << shift) - 1u) & ~0xFFFFu;
     const unsigned grid = (unsigned)sms() * 8;
-    const unsigned sgrid = (unsigned)std::min<uint64_t>(grid, (max_steps + 7) / 8 + 1);  // 8 warps (runs) per CTA
+    const unsigned sgrid = (unsigned)std::min<uint64_t>(grid, (n_tasks + 7) / 8 + 1);  // 8 warps (tasks) per CTA
     for (int b = 0; b < part->n_buckets; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
         if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table);

@@ -215,7 +215,7 @@ def test_device_validity_rebuild_from_exceptions(ctx):
     """lrb_dev_fill_valid (read lengths + sparse exceptions) reproduces the host bitmap; the host path that ships
     exceptions instead of the bitmap gives the same profiles as the one that ships the bitmap."""
     from lrbinner_b200.profile import dev_fill_valid
-    spec = SynthSpec(2000, seed=13, n_rate=2e-3, lowercase_frac=0.01, edge_lengths=True, scale=0.02)
+    spec = SynthSpec(2000, seed=13, n_rate=3e-4, lowercase_frac=0.005, edge_lengths=True, scale=0.02)
     pr = spec.host_packed(threads=4)
     blk, word = pr.exceptions()
     assert 0 < len(blk) < pr.n_blocks // 16
