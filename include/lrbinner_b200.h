@@ -130,6 +130,10 @@ int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_si
  *                   sums[r] is rewritten as the sum of hist row r for r < n_reads (hist and sums must have been
  *                   zeroed together and only ever updated by lrb_dev_search / this call)
  *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
+ *   mode bit 2 (4): count through shared memory — each bucket's list is split once more into 2-byte lists per
+ *                   2^15-key sub-slice (workspace `sub`, sub_capacity entries, fixed share per sub-slice) whose
+ *                   counters live in one SM's shared memory; a bucket whose key skew overflows a share falls back to
+ *                   the L2-atomic kernel.  Same table either way.  Ignored when `sub` is NULL.
  * begin() resets the lists; add() appends the windows of blocks [blk_lo, blk_hi) as one chunk (up to 64 chunks,
  * e.g. one per host-to-device copy so partitioning overlaps the transfer); build() = begin + one add.  A
  * partition can be applied several times (count, exchange tables between GPUs, then search).  Everything is
@@ -149,7 +153,9 @@ typedef struct {
     uint32_t* keys;                /* device, capacity entries */
     unsigned long long* small;     /* device scratch, LRB_PART_SMALL_U64 u64 */
     uint32_t* steps;               /* device, lrb_partition_steps_words(step_capacity) u32 */
+    uint16_t* sub;                 /* device, sub_capacity u16 (optional: second-level lists of the shared-memory count) */
     uint64_t capacity;
+    uint64_t sub_capacity;
     uint64_t step_capacity;
     uint64_t steps_used, n_reads;
     int n_buckets, shift, has_rids, n_chunks;
@@ -179,6 +185,12 @@ int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, const uint6
  * value = count/max(1,total) resp. count/sum with the <1e-4 -> 0 rule (kmer_utils.h:75-84). */
 int lrb_dev_format_composition(const uint32_t* counts, const uint32_t* read_len, uint64_t n_reads, int k, char* text,
                                void* stream);
+/* The same values as float64 on the device — out[N*width] = float("%f" text of count/denominator), i.e. exactly what
+ * stage 3_1 (pipelines.py:310-330) parses back out of com_profs / cov_profs and ae_utils.make_data_loader
+ * (ae_utils.py:19-32) consumes.  k = 3/4/5: composition (denom = read_len, width = 32/136/512);
+ * k = 0: coverage (denom = sums, width = bins, `< 1e-4 -> 0` rule). */
+int lrb_dev_profile_values(const uint32_t* counts, const uint32_t* denom, uint64_t n_reads, int width, int k, double* out,
+                           void* stream);
 int lrb_dev_format_coverage(const uint32_t* hist, const uint32_t* sums, uint64_t n_reads, int bins, char* text,
                             void* stream);
 

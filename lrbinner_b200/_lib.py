@@ -30,8 +30,8 @@ class ReadsView(C.Structure):
 
 class Partition(C.Structure):
     """lrb_partition: caller-owned device buffers + the bucket layout filled by lrb_dev_partition_begin/add."""
-    _fields_ = [("keys", C.c_void_p), ("small", C.c_void_p), ("steps", C.c_void_p), ("capacity", C.c_uint64),
-                ("step_capacity", C.c_uint64), ("steps_used", C.c_uint64), ("n_reads", C.c_uint64),
+    _fields_ = [("keys", C.c_void_p), ("small", C.c_void_p), ("steps", C.c_void_p), ("sub", C.c_void_p), ("capacity", C.c_uint64),
+                ("sub_capacity", C.c_uint64), ("step_capacity", C.c_uint64), ("steps_used", C.c_uint64), ("n_reads", C.c_uint64),
                 ("n_buckets", C.c_int), ("shift", C.c_int), ("has_rids", C.c_int), ("n_chunks", C.c_int),
                 ("key_lo", C.c_uint32), ("key_hi", C.c_uint32),
                 ("chunk_step0", C.c_uint32 * 64), ("chunk_nsteps", C.c_uint32 * 64)]
@@ -81,6 +81,7 @@ _SIG = {
     "lrb_dev_pack_ascii": (C.c_int, [C.POINTER(ReadsView), _P, _P, _P]),
     "lrb_dev_format_composition": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
     "lrb_dev_format_coverage": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
+    "lrb_dev_profile_values": (C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, _P, _P]),
     "lrb_dev_synth": (C.c_int, [C.POINTER(ReadsView), C.POINTER(SynthParams), _P, _P, _P]),
     "lrb_synth_host": (C.c_int, [C.POINTER(SynthParams), _P, _P, _P, C.c_uint64, _P, _P]),
     "lrb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),

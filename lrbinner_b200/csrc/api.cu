@@ -74,7 +74,7 @@ struct lrb_ctx {
     cudaEvent_t sync_ev[LRB_PART_MAX_CHUNKS + 2] = {};  // [0] index arrays, [1..] H2D chunks, [last] composition D2H
     DevBuf codes, valid, read_len, read_blk, tile_read, tile_blk;
     DevBuf table, comp, hist, sums, text;
-    DevBuf part_keys, part_small, part_steps, blk_read;  // L2-resident (partitioned) table passes
+    DevBuf part_keys, part_small, part_steps, part_sub, blk_read;  // L2-resident (partitioned) table passes
     DevBuf exc_blk, exc_valid;                            // validity exceptions (lrb_dev_fill_valid)
     lrb_partition part = {};
     bool table_ready = false;  // holds a complete (mirrored) table
@@ -120,7 +120,7 @@ extern "C" void lrb_ctx_destroy(lrb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->codes, &c->valid, &c->read_len, &c->read_blk, &c->tile_read, &c->tile_blk, &c->table, &c->comp,
-                      &c->hist, &c->sums, &c->text, &c->part_keys, &c->part_small, &c->part_steps, &c->blk_read, &c->exc_blk, &c->exc_valid})
+                      &c->hist, &c->sums, &c->text, &c->part_keys, &c->part_small, &c->part_steps, &c->part_sub, &c->blk_read, &c->exc_blk, &c->exc_valid})
         b->release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->sync_ev) if (ev) cudaEventDestroy(ev);
@@ -230,6 +230,20 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             c->part.small = (unsigned long long*)c->part_small.p;
             c->part.capacity = cap;
             c->part.step_capacity = step_cap;
+            // second-level lists for the shared-memory count: worth it once the read set is large; optional
+            c->part.sub = nullptr;
+            c->part.sub_capacity = 0;
+            const char* e = getenv("LRB_COUNT_PATH");
+            const bool want_smem = e ? !strcmp(e, "smem") : nb >= (1u << 19);
+            if (do_count && want_smem && !(e && !strcmp(e, "l2"))) {
+                const size_t sub_cap = std::max<size_t>(cap / 4, 1u << 16);
+                if (c->part_sub.reserve(sizeof(uint16_t) * sub_cap) == LRB_OK) {
+                    c->part.sub = (uint16_t*)c->part_sub.p;
+                    c->part.sub_capacity = sub_cap;
+                } else {
+                    cudaGetLastError();
+                }
+            }
         }
     }
     lrb_reads_view& v = c->dview;
@@ -316,7 +330,7 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
     }
     CTX_CUDA(cudaEventRecord(c->sync_ev[LRB_PART_MAX_CHUNKS + 1], sout));
     if (use_part) {
-        const int mode = (do_count ? 1 : 0) | (do_search && n ? 2 : 0);
+        const int mode = (do_count ? 1 : 0) | (do_search && n ? 2 : 0) | (do_count && c->part.sub ? 4 : 0);
         if (mode && (rc = lrb_dev_partition_apply(&c->part, mode, (uint32_t*)c->table.p, bin_size, bins, (uint32_t*)c->hist.p,
                                                   (uint32_t*)c->sums.p, st)))
             return rc;

@@ -6,6 +6,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,28 +37,38 @@ namespace {
 //    after '+' or a length mismatch ends the stream WITHOUT emitting the record (kseq.h:209-214);
 //  * the tools copy the sequence as a C string (io_utils.h:159): it is cut at the first NUL byte.
 struct Record {
-    uint64_t off;  // into `pool`
+    uint64_t off;    // into the file image (in_pool == 0) or into the parsing thread's pool
     uint32_t len;
+    uint32_t in_pool;
 };
 
 static inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
 struct Parsed {
-    std::string pool;  // concatenated sequences
+    std::string pool;  // sequences that span several lines, concatenated (single-line ones stay in the file image)
     std::vector<Record> recs;
 };
 
-static void parse_records(const unsigned char* buf, size_t n, Parsed& out) {
-    size_t pos = 0;
+// Parses the records whose header character lies in [pos, limit).  `pos` is either 0 (the start of the stream) or
+// the position of a header character.  Returns the position of the first header character at or beyond `limit`
+// (where the next range starts) or n; *ended is set when the stream ends here for good (end of data, or a FASTQ
+// record without its quality block / with a length mismatch, which makes kseq stop silently).
+static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t limit, Parsed& out, bool* ended) {
     int pending = 0;  // header char already consumed
     std::string qual;
+    *ended = false;
     while (true) {
+        size_t hdr;
         if (!pending) {
             while (pos < n && buf[pos] != '>' && buf[pos] != '@') ++pos;
-            if (pos >= n) return;
+            if (pos >= n) { *ended = true; return n; }
+            hdr = pos;
             pending = buf[pos++];
+        } else {
+            hdr = pos - 1;
         }
-        if (pos >= n) return;  // nothing after the header char
+        if (hdr >= limit) return hdr;
+        if (pos >= n) { *ended = true; return n; }  // nothing after the header char
         // name
         size_t i = pos;
         while (i < n && !is_space(buf[i])) ++i;
@@ -67,28 +78,43 @@ static void parse_records(const unsigned char* buf, size_t n, Parsed& out) {
             const void* nl = pos < n ? memchr(buf + pos, '\n', n - pos) : nullptr;
             pos = nl ? (size_t)((const unsigned char*)nl - buf) + 1 : n;
         }
-        // sequence
-        const size_t seq_off = out.pool.size();
+        // sequence: the first line stays where it is; a second line moves the record into the pool
+        const size_t pool_off = out.pool.size();
+        size_t first_off = 0, acc = 0;  // acc = accumulated length
+        bool multi = false;
         int c = -1;
         while (true) {
             if (pos >= n) { c = -1; break; }
             c = buf[pos++];
             if (c == '>' || c == '+' || c == '@') break;
             if (c == '\n') continue;
-            out.pool.push_back((char)c);
+            const size_t ls = pos - 1;  // line start (the char just read belongs to the sequence)
+            size_t le = pos;
             if (pos < n) {
                 const void* nl = memchr(buf + pos, '\n', n - pos);
-                const size_t e = nl ? (size_t)((const unsigned char*)nl - buf) : n;
-                out.pool.append((const char*)buf + pos, e - pos);
-                pos = nl ? e + 1 : n;
-                if (out.pool.size() - seq_off > 1 && out.pool.back() == '\r') out.pool.pop_back();
+                le = nl ? (size_t)((const unsigned char*)nl - buf) : n;
+                pos = nl ? le + 1 : n;
+            }
+            // kseq appends the first char, then the rest of the line, then drops one trailing CR if more than one byte
+            // has been accumulated — except when the line was cut by end of data right after its first char
+            const bool appended_rest = ls + 1 < n;
+            size_t len = le - ls;
+            if (acc == 0 && !multi) {
+                first_off = ls;
+                acc = len;
+                if (appended_rest && acc > 1 && buf[ls + acc - 1] == '\r') --acc;
+            } else {
+                if (!multi) { out.pool.append((const char*)buf + first_off, acc); multi = true; }
+                out.pool.append((const char*)buf + ls, len);
+                acc += len;
+                if (appended_rest && acc > 1 && out.pool.back() == '\r') { out.pool.pop_back(); --acc; }
             }
         }
         if (c == '>' || c == '@') pending = c;
-        size_t seq_len = out.pool.size() - seq_off;
+        size_t seq_len = acc;
         if (c == '+') {
             const void* nl = pos < n ? memchr(buf + pos, '\n', n - pos) : nullptr;
-            if (!nl) { out.pool.resize(seq_off); return; }  // no quality block: stream ends, record dropped
+            if (!nl) { out.pool.resize(pool_off); *ended = true; return n; }  // no quality block: stream ends, record dropped
             pos = (size_t)((const unsigned char*)nl - buf) + 1;
             qual.clear();
             while (pos < n) {
@@ -100,23 +126,105 @@ static void parse_records(const unsigned char* buf, size_t n, Parsed& out) {
                 if (!(qual.size() < seq_len)) break;
             }
             pending = 0;
-            if (qual.size() != seq_len) { out.pool.resize(seq_off); return; }
+            if (qual.size() != seq_len) { out.pool.resize(pool_off); *ended = true; return n; }
         }
         // C-string copy: cut at the first NUL
+        const unsigned char* sp = multi ? (const unsigned char*)out.pool.data() + pool_off : buf + first_off;
         if (seq_len) {
-            const void* z = memchr(out.pool.data() + seq_off, 0, seq_len);
+            const void* z = memchr(sp, 0, seq_len);
             if (z) {
-                seq_len = (size_t)((const char*)z - (out.pool.data() + seq_off));
-                out.pool.resize(seq_off + seq_len);
+                seq_len = (size_t)((const unsigned char*)z - sp);
+                if (multi) out.pool.resize(pool_off + seq_len);
             }
         }
-        if (seq_len > 0xFFFFFFFFull) { out.pool.resize(seq_off); return; }  // > 4 Gbase record: not representable
-        out.recs.push_back(Record{seq_off, (uint32_t)seq_len});
+        if (seq_len > 0xFFFFFFFFull) { out.pool.resize(pool_off); *ended = true; return n; }  // > 4 Gbase record: not representable
+        out.recs.push_back(Record{multi ? (uint64_t)pool_off : (uint64_t)first_off, (uint32_t)seq_len, multi ? 1u : 0u});
     }
 }
 
-static bool read_whole_file(const char* path, std::vector<unsigned char>& data) {
-    gzFile f = gzopen(path, "rb");  // transparent for uncompressed input, like io_utils.h:143
+// Candidate start of a range: the first header-looking line start at or after `from` ('\n' then '>' or '@'; for '@'
+// the line after next must start with '+', which rules out nearly every quality line that happens to begin with '@').
+// Only a guess — parse_all checks it against the parse of the preceding range.
+static size_t find_candidate(const unsigned char* buf, size_t n, size_t from) {
+    size_t p = from ? from : 1;
+    while (p < n) {
+        const void* nl = memchr(buf + p - 1, '\n', n - (p - 1));
+        if (!nl) return n;
+        p = (size_t)((const unsigned char*)nl - buf) + 1;
+        if (p >= n) return n;
+        if (buf[p] == '>') return p;
+        if (buf[p] == '@') {
+            const void* l1 = memchr(buf + p, '\n', n - p);
+            const void* l2 = l1 ? memchr((const unsigned char*)l1 + 1, '\n', n - ((const unsigned char*)l1 + 1 - buf)) : nullptr;
+            if (!l2 || (size_t)((const unsigned char*)l2 + 1 - buf) >= n || ((const unsigned char*)l2)[1] == '+') return p;
+        }
+        ++p;
+    }
+    return n;
+}
+
+// Whole-stream parse on `threads` threads: ranges start at guessed record boundaries and are parsed speculatively;
+// a sequential pass then keeps a range's result only if the preceding range really ended on its start, and
+// re-parses it from the true boundary otherwise.  The outcome equals parse_range(0, n) by construction.
+static void parse_all(const unsigned char* buf, size_t n, int threads, size_t min_chunk, std::vector<Parsed>& parts) {
+    parts.clear();
+    size_t nr = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n / std::max<size_t>(min_chunk, 1)));
+    if (nr == 1) {
+        parts.resize(1);
+        bool ended;
+        parse_range(buf, n, 0, n, parts[0], &ended);
+        return;
+    }
+    std::vector<size_t> start(nr + 1);
+    start[0] = 0;
+    for (size_t t = 1; t < nr; ++t) start[t] = std::max(start[t - 1], find_candidate(buf, n, n / nr * t));
+    start[nr] = n;
+    std::vector<Parsed> spec(nr);
+    std::vector<size_t> next(nr);
+    std::vector<char> ended(nr);
+    {
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nr; ++t)
+            pool.emplace_back([&, t]() {
+                bool e = false;
+                next[t] = start[t] < start[t + 1] ? parse_range(buf, n, start[t], start[t + 1], spec[t], &e) : start[t];
+                ended[t] = e;
+            });
+        for (auto& th : pool) th.join();
+    }
+    size_t cur = next[0];
+    bool done = ended[0];
+    parts.push_back(std::move(spec[0]));
+    for (size_t t = 1; t < nr && !done; ++t) {
+        if (start[t] >= start[t + 1]) continue;   // empty range
+        if (cur >= start[t + 1]) continue;        // the previous record runs past this whole range
+        if (cur == start[t]) {
+            cur = next[t];
+            done = ended[t];
+            parts.push_back(std::move(spec[t]));
+        } else {                                   // the guess was not a record boundary: parse from the real one
+            Parsed fix;
+            bool e = false;
+            cur = parse_range(buf, n, cur, start[t + 1], fix, &e);
+            done = e;
+            parts.push_back(std::move(fix));
+        }
+    }
+}
+
+// The decompressed file image: a private mapping for plain files, a heap buffer for gzip (zlib's gzread, like
+// io_utils.h:143; a plain file passes through gzread unchanged, so mapping it is equivalent).
+struct FileImage {
+    const unsigned char* data = nullptr;
+    size_t size = 0;
+    void* map = nullptr;
+    size_t map_len = 0;
+    std::vector<unsigned char> heap;
+    ~FileImage() { if (map) munmap(map, map_len); }
+};
+
+static bool read_gz(const char* path, std::vector<unsigned char>& data) {
+    gzFile f = gzopen(path, "rb");
     if (!f) return false;
     gzbuffer(f, 1 << 20);
     size_t n = 0;
@@ -133,6 +241,31 @@ static bool read_whole_file(const char* path, std::vector<unsigned char>& data) 
     return true;
 }
 
+static void load_file(const char* path, FileImage& img) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return;  // unreadable file == empty stream (tools: exit 0, empty outputs)
+    struct stat st;
+    unsigned char magic[2] = {0, 0};
+    const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+    const bool gz = regular && st.st_size >= 2 && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (regular && !gz && st.st_size > 0) {
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
+            madvise(m, (size_t)st.st_size, MADV_WILLNEED);
+            img.map = m;
+            img.map_len = img.size = (size_t)st.st_size;
+            img.data = (const unsigned char*)m;
+            close(fd);
+            return;
+        }
+    }
+    close(fd);
+    if (read_gz(path, img.heap)) {
+        img.data = img.heap.data();
+        img.size = img.heap.size();
+    }
+}
+
 // ---- packing -----------------------------------------------------------------------------------
 struct PackLut {
     uint8_t code[256];
@@ -146,8 +279,20 @@ struct PackLut {
 };
 static const PackLut g_pack;
 
-static void pack_read(const unsigned char* s, uint32_t len, uint32_t* codes, uint32_t* valid) {
-    // codes/valid point at the read's first block; the read owns len/32 + 1 blocks (pre-zeroed)
+static void pack_tail(const unsigned char* p, uint32_t rem, uint32_t* codes2, uint32_t* valid1) {
+    uint32_t w0 = 0, w1 = 0, v = 0;
+    for (uint32_t j = 0; j < rem; ++j) {
+        const uint32_t code = g_pack.code[p[j]];
+        if (j < 16) w0 |= code << (30 - 2 * j); else w1 |= code << (62 - 2 * j);
+        v |= (uint32_t)g_pack.ok[p[j]] << j;
+    }
+    codes2[0] = w0;
+    codes2[1] = w1;
+    *valid1 = v;
+}
+
+static void pack_read_scalar(const unsigned char* s, uint32_t len, uint32_t* codes, uint32_t* valid) {
+    // codes/valid point at the read's first block; the read owns len/32 + 1 blocks, every one of which is written
     const uint32_t full = len / 32;
     for (uint32_t b = 0; b < full; ++b) {
         const unsigned char* p = s + (size_t)b * 32;
@@ -162,17 +307,42 @@ static void pack_read(const unsigned char* s, uint32_t len, uint32_t* codes, uin
         codes[2 * (size_t)b + 1] = w1;
         valid[b] = v;
     }
-    const uint32_t rem = len - full * 32;
-    uint32_t w0 = 0, w1 = 0, v = 0;
-    const unsigned char* p = s + (size_t)full * 32;
-    for (uint32_t j = 0; j < rem; ++j) {
-        const uint32_t code = g_pack.code[p[j]];
-        if (j < 16) w0 |= code << (30 - 2 * j); else w1 |= code << (62 - 2 * j);
-        v |= (uint32_t)g_pack.ok[p[j]] << j;
+    pack_tail(s + (size_t)full * 32, len - full * 32, codes + 2 * (size_t)full, valid + full);
+}
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+// 32 bases per step: the two code bits of every byte (bits 1-2) are gathered with PEXT after a byte swap (first base
+// -> most significant pair), validity = four byte compares + MOVEMASK (bit j <-> byte j, the layout of `valid`).
+__attribute__((target("avx2,bmi2"))) static void pack_read_avx2(const unsigned char* s, uint32_t len, uint32_t* codes, uint32_t* valid) {
+    const uint32_t full = len / 32;
+    const __m256i cA = _mm256_set1_epi8('A'), cC = _mm256_set1_epi8('C'), cG = _mm256_set1_epi8('G'), cT = _mm256_set1_epi8('T');
+    for (uint32_t b = 0; b < full; ++b) {
+        const unsigned char* p = s + (size_t)b * 32;
+        uint64_t q0, q1, q2, q3;
+        memcpy(&q0, p, 8); memcpy(&q1, p + 8, 8); memcpy(&q2, p + 16, 8); memcpy(&q3, p + 24, 8);
+        const uint64_t m = 0x0606060606060606ull;
+        const uint32_t w0 = (uint32_t)(_pext_u64(__builtin_bswap64(q0), m) << 16 | _pext_u64(__builtin_bswap64(q1), m));
+        const uint32_t w1 = (uint32_t)(_pext_u64(__builtin_bswap64(q2), m) << 16 | _pext_u64(__builtin_bswap64(q3), m));
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p));
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(x, cA), _mm256_cmpeq_epi8(x, cC)),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(x, cG), _mm256_cmpeq_epi8(x, cT)));
+        codes[2 * (size_t)b] = w0;
+        codes[2 * (size_t)b + 1] = w1;
+        valid[b] = (uint32_t)_mm256_movemask_epi8(ok);
     }
-    codes[2 * (size_t)full] = w0;
-    codes[2 * (size_t)full + 1] = w1;
-    valid[full] = v;
+    pack_tail(s + (size_t)full * 32, len - full * 32, codes + 2 * (size_t)full, valid + full);
+}
+static const bool g_have_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+#else
+static const bool g_have_avx2 = false;
+static void pack_read_avx2(const unsigned char* s, uint32_t len, uint32_t* codes, uint32_t* valid) { pack_read_scalar(s, len, codes, valid); }
+#endif
+
+static void pack_read(const unsigned char* s, uint32_t len, uint32_t* codes, uint32_t* valid) {
+    static const bool force_scalar = getenv("LRB_PACK_SCALAR") != nullptr;
+    if (g_have_avx2 && !force_scalar) pack_read_avx2(s, len, codes, valid);
+    else pack_read_scalar(s, len, codes, valid);
 }
 
 static void free_reads(lrb_reads* r) {
@@ -188,8 +358,9 @@ static void free_reads(lrb_reads* r) {
     delete r;
 }
 
-// builds read_blk / tiles from read_len and allocates zeroed codes/valid
-static int build_layout(lrb_reads* r) {
+// builds read_blk / tiles from read_len and allocates codes/valid — zeroed only on request: the packers write every
+// word of every block themselves (in parallel, which also spreads the first-touch page faults over the threads)
+static int build_layout(lrb_reads* r, bool zero = false) {
     const uint64_t n = r->n_reads;
     r->read_blk = (uint32_t*)malloc(sizeof(uint32_t) * (n + 1));
     if (!r->read_blk) return lrb_set_error(LRB_ENOMEM, "out of memory (read_blk)");
@@ -228,10 +399,12 @@ static int build_layout(lrb_reads* r) {
         r->codes = (uint32_t*)calloc(2 * blk + 2, 4);
         r->valid = (uint32_t*)calloc(blk + 1, 4);
         if (!r->codes || !r->valid) return lrb_set_error(LRB_ENOMEM, "out of memory (packed stream)");
-    } else {
+    } else if (zero) {
         memset(r->codes, 0, sizeof(uint32_t) * (2 * blk + 2));
         memset(r->valid, 0, sizeof(uint32_t) * (blk + 1));
     }
+    r->codes[2 * blk] = r->codes[2 * blk + 1] = 0;  // the words after the stream
+    r->valid[blk] = 0;
     return LRB_OK;
 }
 
@@ -333,21 +506,45 @@ extern "C" int lrb_reads_exceptions(const lrb_reads* r, const uint32_t** blk, co
 extern "C" int lrb_reads_from_file(const char* path, int threads, lrb_reads** out) {
     if (!path || !out) return lrb_set_error(LRB_EINVAL, "lrb_reads_from_file: null argument");
     *out = nullptr;
-    std::vector<unsigned char> data;
-    read_whole_file(path, data);  // unreadable file == empty stream (tools: exit 0, empty outputs)
-    Parsed parsed;
-    parse_records(data.data(), data.size(), parsed);
-    std::vector<unsigned char>().swap(data);
+    const bool trace = getenv("LRB_INGEST_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    FileImage img;
+    load_file(path, img);
+    const double t1 = now();
+    size_t min_chunk = 8u << 20;  // below this a range is not worth a thread
+    {
+        const char* e = getenv("LRB_PARSE_CHUNK");  // tests force tiny ranges to exercise the boundary logic
+        if (e && atoll(e) > 0) min_chunk = (size_t)atoll(e);
+    }
+    std::vector<Parsed> parts;
+    parse_all(img.data, img.size, threads, min_chunk, parts);
+    const double t2 = now();
+    uint64_t n_reads = 0;
+    for (auto& p : parts) n_reads += p.recs.size();
     lrb_reads* r = new lrb_reads();
-    r->n_reads = parsed.recs.size();
-    r->read_len = (uint32_t*)malloc(sizeof(uint32_t) * (r->n_reads + 1));
+    r->n_reads = n_reads;
+    r->read_len = (uint32_t*)malloc(sizeof(uint32_t) * (n_reads + 1));
     if (!r->read_len) { free_reads(r); return lrb_set_error(LRB_ENOMEM, "out of memory (read_len)"); }
-    for (uint64_t i = 0; i < r->n_reads; ++i) r->read_len[i] = parsed.recs[i].len;
+    std::vector<const unsigned char*> ptr(n_reads + 1);
+    {
+        uint64_t i = 0;
+        for (auto& p : parts)
+            for (const Record& rec : p.recs) {
+                r->read_len[i] = rec.len;
+                ptr[i] = rec.in_pool ? (const unsigned char*)p.pool.data() + rec.off : img.data + rec.off;
+                ++i;
+            }
+    }
     int rc = build_layout(r);
     if (rc) { free_reads(r); return rc; }
-    const unsigned char* pool = (const unsigned char*)parsed.pool.data();
-    pack_all(r, threads, [&](uint64_t i) { return pool + parsed.recs[i].off; });
+    const double t3 = now();
+    pack_all(r, threads, [&](uint64_t i) { return ptr[i]; });
+    const double t4 = now();
     if ((rc = index_valid(r, threads))) { free_reads(r); return rc; }
+    if (trace)
+        fprintf(stderr, "[lrb ingest] %zu bytes, %llu reads: load %.3f s, parse %.3f s (%zu ranges), layout+alloc %.3f s, pack %.3f s, index %.3f s\n",
+                img.size, (unsigned long long)n_reads, t1 - t0, t2 - t1, parts.size(), t3 - t2, t4 - t3, now() - t4);
     *out = r;
     return LRB_OK;
 }
@@ -381,7 +578,7 @@ extern "C" int lrb_reads_from_lengths(const uint32_t* lengths, uint64_t n_reads,
     r->read_len = (uint32_t*)malloc(sizeof(uint32_t) * (n_reads + 1));
     if (!r->read_len) { free_reads(r); return lrb_set_error(LRB_ENOMEM, "out of memory (read_len)"); }
     if (n_reads) memcpy(r->read_len, lengths, sizeof(uint32_t) * n_reads);
-    int rc = build_layout(r);
+    int rc = build_layout(r, true);
     if (rc) { free_reads(r); return rc; }
     *out = r;
     return LRB_OK;

@@ -257,6 +257,19 @@ k_format_rows(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ 
     if (COMP && j == width - 1) dst[9] = '\n';
 }
 
+// profile values as the downstream stages see them: float(the "%f" text) == fixed6 / 10^6 (both exactly rounded)
+template <bool COMP>
+__global__ void __launch_bounds__(256)
+k_profile_values(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ denom_src, uint64_t n_rows, uint32_t width, int k,
+                 double* __restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_rows * width) return;
+    const uint64_t r = idx / width;
+    uint32_t den = denom_src[r];
+    if (COMP) den = den >= (uint32_t)k ? den - (uint32_t)k + 1u : 0u;  // total = max(0, len-k+1)
+    out[idx] = (double)fixed6(counts[idx], den, !COMP) / 1e6;
+}
+
 thread_local bool t_luts_ready[64] = {false};
 
 int ensure_luts() {
@@ -392,6 +405,20 @@ extern "C" int lrb_dev_format_composition(const uint32_t* counts, const uint32_t
     if (!n_reads) return LRB_OK;
     const uint64_t total = n_reads * (uint64_t)P;
     k_format_rows<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, read_len, n_reads, (uint32_t)P, k, text);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+extern "C" int lrb_dev_profile_values(const uint32_t* counts, const uint32_t* denom, uint64_t n_reads, int width, int k, double* out,
+                                      void* stream) {
+    if (width <= 0 || !out || (n_reads && (!counts || !denom))) return lrb_set_error(LRB_EINVAL, "lrb_dev_profile_values: bad argument");
+    if (k != 0 && ((k == 3 ? 32 : k == 4 ? 136 : k == 5 ? 512 : 0) != width))
+        return lrb_set_error(LRB_EINVAL, "lrb_dev_profile_values: width %d does not belong to k = %d", width, k);
+    if (!n_reads) return LRB_OK;
+    const uint64_t total = n_reads * (uint64_t)width;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (k) k_profile_values<true><<<grid, 256, 0, (cudaStream_t)stream>>>(counts, denom, n_reads, (uint32_t)width, k, out);
+    else k_profile_values<false><<<grid, 256, 0, (cudaStream_t)stream>>>(counts, denom, n_reads, (uint32_t)width, 0, out);
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

@@ -48,6 +48,8 @@ constexpr int kStepSlots = kPartThreads * 32;
 constexpr int kMaxBuckets = LRB_PART_MAX_BUCKETS;
 constexpr int kMaxChunks = LRB_PART_MAX_CHUNKS;
 constexpr int kMaxGroups = LRB_PART_MAX_GROUPS;
+constexpr int kSubBits = 15;               // a sub-slice = 2^15 bit-15-clear keys = 128 KB of u32 counters in shared memory
+constexpr int kMaxSubs = 1 << (25 - 16);   // sub-slices per bucket at the largest bucket size (shift 25)
 constexpr uint64_t kMaxChunkBlocks = 1ull << 26;  // 2^31 slots: run offsets inside a chunk's bucket region fit u32
 typedef unsigned long long ull;
 
@@ -58,6 +60,8 @@ struct PartMeta {
     ull chunk_base[kMaxChunks + 1];        // first entry of each chunk's region
     ull needed;                            // entries the chunks added so far need in total
     ull overflow;                          // != 0: capacity exceeded, lists are incomplete (apply does nothing)
+    ull cur2[kMaxSubs];                    // second level: fill cursor of each sub-slice list of the bucket in flight
+    uint32_t overflow2[kMaxBuckets];       // second level: a sub list of bucket b overflowed -> k_count_keys counts b
 };
 static_assert(sizeof(PartMeta) <= sizeof(ull) * LRB_PART_SMALL_U64, "lrb_partition.small too small");
 
@@ -329,8 +333,9 @@ __device__ __forceinline__ uint32_t entry_key(uint32_t e, uint32_t bucket_base, 
 
 __global__ void __launch_bounds__(256)
 k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, uint32_t bucket_base,
-             uint32_t hi_mask2, uint32_t* __restrict__ table) {
+             uint32_t hi_mask2, uint32_t* __restrict__ table, int fallback_only) {
     if (meta->overflow) return;
+    if (fallback_only && !meta->overflow2[bucket]) return;  // the shared-memory path counted this bucket
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (int c = 0; c < n_chunks; ++c) {
         const uint64_t n = meta->counts[c][bucket];
@@ -348,6 +353,153 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
     }
 }
 
+// ---- second level (count only): bucket list -> 2-byte lists per 2^15-key sub-slice -> shared-memory counting ------
+// RED.ADD into an L2-resident slice tops out near 1.3 cycles per lane per SM (~196 G/s on this part,
+// profiles/r01_ubench_roofline.jsonl); shared-memory atomics run ~8x faster.  So for counting, a bucket's list is
+// partitioned once more by the next key bits into sub-slices of 2^15 keys whose counters fit one SM's shared memory.
+// k2_partition: tiles of 8192 entries; per tile count per sub-slice (smem atomics), reserve the tile's share of each
+// sub list with one global atomic per (tile, sub), rank + place into a staging array, sweep it out linearly (the
+// staged word carries its sub-slice).  List order is irrelevant for counting, so no deterministic layout is needed.
+// Sub lists have a fixed capacity C2 (a multiple of the expected size); a bucket whose keys are skewed enough to
+// overflow one raises overflow2[bucket] and is counted by k_count_keys instead (both kernels look at the flag).
+__global__ void __launch_bounds__(256)
+k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int bucket, int n_chunks, int sub_bits,
+             uint16_t* __restrict__ sub16, uint32_t C2) {
+    __shared__ uint32_t s_stage[kStepSlots];  // (sub << 15) | low 15 key bits, grouped by sub-slice
+    __shared__ uint32_t s_cnt[kMaxSubs];      // count, then staging cursor
+    __shared__ uint32_t s_delta[kMaxSubs];    // list position of staged position i of sub-slice s = i + s_delta[s]
+    __shared__ uint32_t s_wsum[8];
+    if (meta->overflow) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t nsub = 1u << sub_bits, sub_mask = nsub - 1u;
+    const uint32_t limit = nsub * C2;
+    uint64_t total_tiles = 0;
+    for (int c = 0; c < n_chunks; ++c) total_tiles += (meta->counts[c][bucket] + kStepSlots - 1) / kStepSlots;
+    for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int c = 0;
+        uint64_t t = tile;
+        for (;; ++c) {
+            const uint64_t tc = (meta->counts[c][bucket] + kStepSlots - 1) / kStepSlots;
+            if (t < tc) break;
+            t -= tc;
+        }
+        const uint64_t n_reg = meta->counts[c][bucket];
+        const uint32_t n_tile = (uint32_t)min((uint64_t)kStepSlots, n_reg - t * kStepSlots);
+        const uint32_t* __restrict__ src = ents + meta->offsets[c][bucket] + t * kStepSlots;
+        s_cnt[tid] = 0;
+        s_cnt[tid + 256] = 0;
+        __syncthreads();
+        // the tile is read twice (count, then rank + place; the second read hits L2) instead of parking 32 entries
+        // per thread in registers across the barriers: 3x the resident warps.  Loads go out eight at a time.
+        const bool full = n_tile == kStepSlots;
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = (j0 + u) * 256u + tid;
+                v[u] = (full || i < n_tile) ? __ldg(src + i) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (full || (j0 + u) * 256u + tid < n_tile) atomicAdd(&s_cnt[(v[u] >> kSubBits) & sub_mask], 1u);
+        }
+        __syncthreads();
+        {   // exclusive scan over the sub-slices (two per thread), reservation in the global lists
+            const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+            uint32_t x = c0 + c1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            if (lane == 31) s_wsum[warp] = x;
+            __syncthreads();
+            uint32_t base = 0;
+            for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
+            const uint32_t ex0 = base + x - c0 - c1, ex1 = ex0 + c0;
+            if (c0) {
+                const ull g = atomicAdd(&meta->cur2[2 * tid], (ull)c0);
+                if (g + c0 > C2) meta->overflow2[bucket] = 1u;
+                s_delta[2 * tid] = (2 * tid) * C2 + (uint32_t)g - ex0;
+            }
+            if (c1) {
+                const ull g = atomicAdd(&meta->cur2[2 * tid + 1], (ull)c1);
+                if (g + c1 > C2) meta->overflow2[bucket] = 1u;
+                s_delta[2 * tid + 1] = (2 * tid + 1) * C2 + (uint32_t)g - ex1;
+            }
+            s_cnt[2 * tid] = ex0;
+            s_cnt[2 * tid + 1] = ex1;
+        }
+        __syncthreads();
+        for (int j0 = 0; j0 < 32; j0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = (j0 + u) * 256u + tid;
+                v[u] = (full || i < n_tile) ? __ldcs(src + i) : 0xFFFFFFFFu;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (full || (j0 + u) * 256u + tid < n_tile) {
+                    const uint32_t sub = (v[u] >> kSubBits) & sub_mask;
+                    const uint32_t idx = atomicAdd(&s_cnt[sub], 1u);
+                    s_stage[idx] = (sub << kSubBits) | (v[u] & ((1u << kSubBits) - 1u));
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n_tile; i += 256) {
+            const uint32_t r = s_stage[i];
+            const uint32_t pos = s_delta[r >> kSubBits] + i;
+            if (pos < limit) sub16[pos] = (uint16_t)(r & ((1u << kSubBits) - 1u));  // out of range only in an overflowed bucket
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per sub-slice: its list -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
+__global__ void __launch_bounds__(1024)
+k_count_smem(const uint16_t* __restrict__ sub16, PartMeta* __restrict__ meta, int bucket, uint32_t C2, uint32_t bucket_base,
+             uint32_t* __restrict__ table) {
+    extern __shared__ uint32_t s_tab[];  // 2^15
+    const uint32_t tid = threadIdx.x, sub = blockIdx.x;
+    const bool skip = meta->overflow || meta->overflow2[bucket];
+    const uint64_t n = meta->cur2[sub];
+    __syncthreads();
+    if (tid == 0) meta->cur2[sub] = 0;  // ready for the next bucket's k2_partition
+    if (skip || n == 0) return;
+    uint4* tab4 = reinterpret_cast<uint4*>(s_tab);
+    for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) tab4[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint16_t* __restrict__ src = sub16 + (size_t)sub * C2;
+    const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
+    const uint32_t n8 = (uint32_t)(n / 8);
+    auto bump8 = [&](const uint4& v) {
+        atomicAdd(&s_tab[v.x & 0xFFFFu], 1u); atomicAdd(&s_tab[v.x >> 16], 1u);
+        atomicAdd(&s_tab[v.y & 0xFFFFu], 1u); atomicAdd(&s_tab[v.y >> 16], 1u);
+        atomicAdd(&s_tab[v.z & 0xFFFFu], 1u); atomicAdd(&s_tab[v.z >> 16], 1u);
+        atomicAdd(&s_tab[v.w & 0xFFFFu], 1u); atomicAdd(&s_tab[v.w >> 16], 1u);
+    };
+    uint32_t i = tid;
+    for (; i + 3 * 1024 < n8; i += 4 * 1024) {  // four 16-byte loads in flight per thread
+        const uint4 v0 = __ldcs(src4 + i), v1 = __ldcs(src4 + i + 1024), v2 = __ldcs(src4 + i + 2048), v3 = __ldcs(src4 + i + 3072);
+        bump8(v0); bump8(v1); bump8(v2); bump8(v3);
+    }
+    for (; i < n8; i += 1024) bump8(__ldcs(src4 + i));
+    for (uint32_t k = n8 * 8 + tid; k < n; k += 1024) atomicAdd(&s_tab[src[k]], 1u);
+    __syncthreads();
+    uint4* slice4 = reinterpret_cast<uint4*>(table + bucket_base + (sub << 16));
+    uint4 t4[8];  // 8192 uint4 per slice, eight per thread: all loads first
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t4[u] = slice4[tid + 1024 * u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const uint4 a = tab4[tid + 1024 * u];
+        t4[u].x += a.x; t4[u].y += a.y; t4[u].z += a.z; t4[u].w += a.w;
+        slice4[tid + 1024 * u] = t4[u];
+    }
+}
+
 // entries of one bucket: hist[read][bin(table[key])] += 1.  A warp task is kTaskRuns consecutive runs of one chunk —
 // one contiguous span of the bucket's region — streamed 128 entries per step (four gathers in flight per lane; the
 // kernel is bound by the latency of the dependent stream-load -> gather chain otherwise).  The run boundaries and
@@ -355,20 +507,30 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
 // its entries.  Equal (read, bin) entries of a warp share one RED.  Tasks are numbered across all chunks
 // (L.task0 = prefix of tasks per chunk) so small chunks still fill the machine.
 constexpr uint32_t kTaskRuns = 16;
+constexpr uint32_t kBinLut = 2048;  // counts below this go through a shared-memory bin table when (B+1)*S fits
 
+template <bool USE_LUT>
 __global__ void __launch_bounds__(256)
 k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, ChunkList L,
               StepTables T, uint32_t bucket_base, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
               uint64_t magic, uint32_t B, uint32_t* __restrict__ hist) {
     __shared__ uint32_t s_bnd[8][kTaskRuns + 1];  // per warp: start of each run of the span, [kTaskRuns] = end of the span
-    __shared__ uint32_t s_r0[8][kTaskRuns];       // per warp: read index of the first block of each run's step
+    __shared__ uint32_t s_r0[8][kTaskRuns];       // per warp: read index of each run's step relative to the span's first
+    __shared__ uint16_t s_lut[USE_LUT ? kBinLut : 2];
     if (meta->overflow) return;
+    // every count >= (B+1)*S lands in the last bin (pos >= B), so the table covers the whole rule
+    const uint32_t lut_top = USE_LUT ? (B + 1u) * S32 : 0u;
+    if (USE_LUT) {
+        for (uint32_t i = threadIdx.x; i <= lut_top; i += blockDim.x) s_lut[i] = (uint16_t)coverage_bin(i, S32, magic, B);
+        __syncthreads();
+    }
     const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t* __restrict__ off_row = T.off + (size_t)bucket * T.cap;
     uint32_t* bnd = s_bnd[wl];
     uint32_t* r0 = s_r0[wl];
     const uint32_t n_tasks = L.task0[n_chunks];
+    const int rsh = shift - 1;
     int c = 0;
     for (uint32_t task = warp; task < n_tasks; task += n_warps) {
         while (task >= L.task0[c + 1]) ++c;  // tasks ascend: the chunk index only moves forward
@@ -377,11 +539,35 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
         const uint32_t* __restrict__ region = ents + meta->offsets[c][bucket];
         __syncwarp();
         if (lane <= kTaskRuns) bnd[lane] = __ldg(off_row + s0 + min(sb + lane, ns));  // off_row[s0 + ns] is the terminal offset
-        if (lane < kTaskRuns) r0[lane] = __ldg(T.rid0 + s0 + min(sb + lane, ns - 1u));
+        const uint32_t my_r0 = __ldg(T.rid0 + s0 + min(sb + min(lane, kTaskRuns - 1u), ns - 1u));
+        const uint32_t rbase = __shfl_sync(0xFFFFFFFFu, my_r0, 0);
+        if (lane < kTaskRuns) r0[lane] = my_r0 - rbase;
         __syncwarp();
-        const uint32_t span_beg = bnd[0], span_end = bnd[kTaskRuns], rbase = r0[0];
-        uint32_t cur = 0;  // run of this lane's current entry
-        for (uint32_t i0 = span_beg; i0 < span_end; i0 += 128) {
+        const uint32_t span_beg = bnd[0], span_end = bnd[kTaskRuns];
+        uint32_t* __restrict__ hbase = hist + (size_t)rbase * B;
+        uint32_t cur = 0, nxt = bnd[1], rr = 0;  // run of this lane's current entry, its end, its relative read base
+        auto emit = [&](uint32_t e, uint32_t cnt, uint32_t i, bool act) {
+            uint32_t cell = 0xFFFFFFFFu;
+            if (act) {
+                while (i >= nxt) { ++cur; nxt = bnd[cur + 1]; rr = r0[cur]; }  // runs may be empty; i < bnd[kTaskRuns] bounds cur
+                const uint32_t bin = USE_LUT ? s_lut[min(cnt, lut_top)] : coverage_bin(cnt, S32, magic, B);
+                cell = (rr + (e >> rsh)) * B + bin;
+            }
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cell);
+            if (act && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hbase + cell, (uint32_t)__popc(peers));
+        };
+        uint32_t i0 = span_beg;
+        for (; i0 + 128u <= span_end; i0 += 128u) {  // full steps: no predicates
+            const uint32_t* src = region + i0 + lane;
+            const uint32_t e0 = __ldcs(src), e1 = __ldcs(src + 32), e2 = __ldcs(src + 64), e3 = __ldcs(src + 96);
+            const uint32_t c0 = table[entry_key(e0, bucket_base, hi_mask2)], c1 = table[entry_key(e1, bucket_base, hi_mask2)],
+                           c2 = table[entry_key(e2, bucket_base, hi_mask2)], c3 = table[entry_key(e3, bucket_base, hi_mask2)];
+            emit(e0, c0, i0 + lane, true);
+            emit(e1, c1, i0 + lane + 32u, true);
+            emit(e2, c2, i0 + lane + 64u, true);
+            emit(e3, c3, i0 + lane + 96u, true);
+        }
+        if (i0 < span_end) {  // tail of the span
             uint32_t e[4], cnt[4];
             bool act[4];
 #pragma unroll
@@ -391,18 +577,11 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
                 e[u] = act[u] ? __ldcs(region + i) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? table[entry_key(e[u], bucket_base, hi_mask2)] : 0u;  // L2-resident slice
+            for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? table[entry_key(e[u], bucket_base, hi_mask2)] : 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (i0 + 32u * u >= span_end) break;  // warp-uniform
-                const uint32_t i = i0 + 32u * u + lane;
-                uint32_t cell = 0xFFFFFFFFu;
-                if (act[u]) {
-                    while (i >= bnd[cur + 1]) ++cur;   // runs may be empty; cur < kTaskRuns because i < bnd[kTaskRuns]
-                    cell = (r0[cur] - rbase + (e[u] >> (shift - 1))) * B + coverage_bin(cnt[u], S32, magic, B);
-                }
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cell);
-                if (act[u] && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hist + (size_t)rbase * B + cell, (uint32_t)__popc(peers));
+                emit(e[u], cnt[u], i0 + 32u * u + lane, act[u]);
             }
         }
     }
@@ -548,6 +727,11 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
                                        uint32_t* hist, uint32_t* sums, void* stream) {
     if (!part || !table) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: null argument");
     const bool do_count = mode & 1, do_search = mode & 2;
+    // second-level (shared-memory) counting needs the sub-list workspace; without it the L2-atomic kernel does the job
+    const int sub_bits = part->shift - 16;
+    uint64_t C2 = (part->sub && sub_bits >= 0) ? ((part->sub_capacity >> sub_bits) & ~7ull) : 0;
+    if (C2 << sub_bits >= (1ull << 32)) C2 = (((1ull << 32) - 8) >> sub_bits) & ~7ull;
+    const bool smem_count = do_count && (mode & 4) && C2 >= 64;
     if (do_search) {
         if (!hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: search needs hist and sums");
         if (!part->has_rids) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: partition was built without read ids");
@@ -572,12 +756,25 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const uint32_t hi_mask2 = ((1u << shift) - 1u) & ~0xFFFFu;
     const unsigned grid = (unsigned)sms() * 8;
     const unsigned sgrid = (unsigned)std::min<uint64_t>(grid, (n_tasks + 7) / 8 + 1);  // 8 warps (tasks) per CTA
+    const bool use_lut = ((uint64_t)bins + 1) * S32 < kBinLut;
+    const unsigned grid2 = (unsigned)sms() * 5;
+    constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
+    if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
     for (int b = 0; b < part->n_buckets; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
-        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table);
-        if (do_search)
-            k_search_keys<<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic,
-                                                 (uint32_t)bins, hist);
+        if (smem_count) {
+            k2_partition<<<grid2, 256, 0, st>>>(part->keys, const_cast<PartMeta*>(meta), b, part->n_chunks, sub_bits, part->sub, (uint32_t)C2);
+            k_count_smem<<<1u << sub_bits, 1024, kSmemTable, st>>>(part->sub, const_cast<PartMeta*>(meta), b, (uint32_t)C2, bucket_base, table);
+        }
+        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table, smem_count ? 1 : 0);
+        if (do_search) {
+            if (use_lut)
+                k_search_keys<true><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32,
+                                                           magic, (uint32_t)bins, hist);
+            else
+                k_search_keys<false><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32,
+                                                            magic, (uint32_t)bins, hist);
+        }
     }
     if (do_search && part->n_reads)
         k_row_sums<<<(unsigned)((part->n_reads + 255) / 256), 256, 0, st>>>(hist, sums, part->n_reads, (uint32_t)bins);

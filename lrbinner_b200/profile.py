@@ -273,18 +273,22 @@ class PartitionWorkspace:
     """Scratch of the L2-resident table passes: 4-byte list entries for up to `capacity` windows, the per-step
     tables, the per-block read index, and the lrb_partition descriptor the C ABI fills."""
 
-    def __init__(self, dr, capacity=None, max_chunks=LRB_MAX_CHUNKS):
+    def __init__(self, dr, capacity=None, max_chunks=LRB_MAX_CHUNKS, sub_capacity=None):
         torch = dr.torch
         self.dr = dr
         self.capacity = int(capacity if capacity is not None else max(dr.n_blocks * 32, 1))
         self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
+        # second-level lists of the shared-memory count (2 B per entry of ONE bucket at a time, with headroom)
+        self.sub_capacity = int(sub_capacity if sub_capacity is not None else max(self.capacity // 4, 1 << 16))
+        self.sub = torch.empty(self.sub_capacity, dtype=torch.int16, device=dr.device) if self.sub_capacity else None
         self.small = torch.zeros(_lib.PART_SMALL_U64, dtype=torch.int64, device=dr.device)
         self.step_capacity = int(lib.lrb_partition_step_capacity(dr.n_blocks, max_chunks))
         self.steps = torch.empty(int(lib.lrb_partition_steps_words(self.step_capacity)), dtype=torch.int32, device=dr.device)
         self.blk_read = torch.empty(max(dr.n_blocks, 1), dtype=torch.int32, device=dr.device)
         check(lib.lrb_dev_fill_blk_read(C.byref(dr.view), C.c_void_p(self.blk_read.data_ptr()), _stream()))
         self.part = _lib.Partition(keys=self.keys.data_ptr(), small=self.small.data_ptr(), steps=self.steps.data_ptr(),
-                                   capacity=self.capacity, step_capacity=self.step_capacity)
+                                   sub=self.sub.data_ptr() if self.sub is not None else None, capacity=self.capacity,
+                                   sub_capacity=self.sub_capacity, step_capacity=self.step_capacity)
 
     def begin(self, with_rids=True, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24):
         check(lib.lrb_dev_partition_begin(C.byref(self.part), 1 if with_rids else 0, key_lo, min(key_hi, _lib.TABLE_ENTRIES),
@@ -318,19 +322,20 @@ class PartitionWorkspace:
         check(lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream()))
         return int(needed.value)
 
-    def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None):
-        mode = (1 if count else 0) | (2 if search else 0)
+    def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None, smem_count=True):
+        """smem_count: count through the second-level, shared-memory path (falls back per bucket on key skew)."""
+        mode = (1 if count else 0) | (2 if search else 0) | (4 if (count and smem_count) else 0)
         check(lib.lrb_dev_partition_apply(C.byref(self.part), mode, C.c_void_p(table.data_ptr()), bin_size, bins,
                                           C.c_void_p(hist.data_ptr()) if hist is not None else None,
                                           C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream()))
 
 
 def dev_table15_partitioned(dr, ws, table, do_count=True, bin_size=1, bins=1, hist=None, sums=None, blk_lo=0, blk_hi=None,
-                            key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24):
+                            key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, smem_count=True):
     """One-shot: partition the windows of [blk_lo, blk_hi) x [key_lo, key_hi), then count and/or search per bucket."""
     search = hist is not None
     ws.build(search, blk_lo, blk_hi, key_lo, key_hi, log2_bucket_keys)
-    ws.apply(table, do_count, search, bin_size, bins, hist, sums)
+    ws.apply(table, do_count, search, bin_size, bins, hist, sums, smem_count=smem_count)
 
 
 def dev_format_composition(counts, read_len, n_reads, k, text):

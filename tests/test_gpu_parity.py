@@ -234,6 +234,33 @@ def test_device_validity_rebuild_from_exceptions(ctx):
     assert int(res_exc["sums"].sum()) > 0
 
 
+def test_device_handoff_to_the_autoencoder_equals_the_file_path(tmp_path, ctx):
+    """the float32 tensors make_data_loader (ae_utils.py:19-32) builds from the text -> float() -> .npy ->
+    MinMaxScaler -> .float() chain, produced on the device from the integer profiles without touching disk."""
+    from sklearn.preprocessing import MinMaxScaler
+    from lrbinner_b200.handoff import profile_values, vae_inputs
+    spec = SynthSpec(1200, seed=17, n_rate=5e-4, lowercase_frac=0.01, edge_lengths=True, scale=0.03)
+    pr = spec.host_packed(threads=4)
+    k, bs, bc = 4, 32, 10
+    res = ctx.profile(pr, k=k, bin_size=bs, bins=bc)
+    com, cov = str(tmp_path / "com_profs"), str(tmp_path / "cov_profs")
+    rl = np.array(pr.read_len, copy=True)
+    assert _lib.lib.lrb_write_composition_txt(com.encode(), _ptr(res["comp"]), _ptr(rl), pr.n_reads, k, 2) == 0
+    assert _lib.lib.lrb_write_coverage_txt(cov.encode(), _ptr(res["hist"]), _ptr(res["sums"]), pr.n_reads, bc, 2) == 0
+    # the reference's chain (pipelines.py:315-321, ae_utils.py:21-25), literally
+    comp_ref = np.array([np.array(list(map(float, line.strip().split()))) for line in open(com) if len(line.strip()) > 0])
+    cov_ref = np.array([np.array(list(map(float, line.strip().split()))) for line in open(cov) if len(line.strip()) > 0])
+    profs_ref = torch.from_numpy(MinMaxScaler().fit_transform(comp_ref)).float()
+    covs_ref = torch.from_numpy(MinMaxScaler().fit_transform(cov_ref)).float()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).to(DEV)
+    comp_d, len_d, hist_d, sums_d = dev(res["comp"]), dev(rl), dev(res["hist"]), dev(res["sums"])
+    assert np.array_equal(profile_values(comp_d, len_d, k).cpu().numpy(), comp_ref)
+    assert np.array_equal(profile_values(hist_d, sums_d, 0).cpu().numpy(), cov_ref)
+    covs, profs = vae_inputs(comp_d, len_d, hist_d, sums_d, k)
+    assert covs.is_cuda and profs.dtype == torch.float32
+    assert torch.equal(covs.cpu(), covs_ref) and torch.equal(profs.cpu(), profs_ref)
+
+
 def test_device_text_epilogue_matches_host_writer(tmp_path, ctx):
     spec = SynthSpec(700, seed=4, n_rate=1e-3, edge_lengths=True, scale=0.02)
     pr = spec.host_packed()
@@ -334,6 +361,18 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     for klo, khi, shift in ((0, 2 ** 26, 20), (2 ** 26, 2 ** 27, 21), (2 ** 27, 2 ** 30, 24)):
         dev_table15_partitioned(dr, ws, table_p, True, bs, bc, hist_p, sums_p, key_lo=klo, key_hi=khi, log2_bucket_keys=shift)
     assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
+    # the shared-memory (second-level) count is the default above; the L2-atomic kernel alone, and a sub-list workspace so
+    # small that every bucket overflows its share and falls back, give the same table; so does accumulating on top
+    for kw in (dict(smem_count=False), dict(smem_count=True)):
+        table_p = z(2 ** 30)
+        dev_table15_partitioned(dr, ws, table_p, True, **kw)
+        assert torch.equal(table_p, table_d), kw
+    tiny = PartitionWorkspace(dr, sub_capacity=1 << 14)   # 64 entries per sub-slice list: most overflow
+    table_p = torch.full((2 ** 30,), 7, dtype=torch.int32, device=DEV)
+    dev_table15_partitioned(dr, tiny, table_p, True)
+    dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=25)
+    assert torch.equal(table_p, 2 * table_d + 7)
+    del tiny
     # workspace too small is an error, not a truncation
     small = PartitionWorkspace(dr, capacity=1000)
     t_small = z(2 ** 30)

@@ -113,7 +113,7 @@ def test_ingest_fuzz_against_oracle(tmp_path):
     alphabet = np.frombuffer(b"ACGTacgtN>@+\n\r \t;-", dtype=np.uint8)
     probs = np.array([8, 8, 8, 8, 1, 1, 1, 1, 1, .6, .6, .6, 4, 1.5, .5, .3, .2, .2])
     probs /= probs.sum()
-    for it in range(300):
+    for it in range(400):
         n = int(rng.integers(0, 400))
         data = rng.choice(alphabet, size=n, p=probs).tobytes()
         if it % 5 == 0:
@@ -123,11 +123,57 @@ def test_ingest_fuzz_against_oracle(tmp_path):
         path = tmp_path / f"f{it}.txt"
         path.write_bytes(data)
         seqs, _ = oracle.parse_reads(data)
-        pr = PackedReads.from_file(str(path), threads=1)
-        assert pr.n_reads == len(seqs), (it, data)
-        assert list(pr.read_len) == [len(s) for s in seqs], (it, data)
-        for i, s in enumerate(seqs):
-            assert pr.unpack(i) == bytes(b"ACTG"[(c >> 1) & 3] for c in s), (it, i)
+        # serial parse, then the speculative multi-range parse with ranges of a few bytes (every guess at a record
+        # boundary that can go wrong does go wrong somewhere in these files)
+        for threads, chunk in ((1, None), (4, 24), (8, 5), (3, 1)):
+            if chunk is None:
+                os.environ.pop("LRB_PARSE_CHUNK", None)
+            else:
+                os.environ["LRB_PARSE_CHUNK"] = str(chunk)
+            try:
+                pr = PackedReads.from_file(str(path), threads=threads)
+            finally:
+                os.environ.pop("LRB_PARSE_CHUNK", None)
+            assert pr.n_reads == len(seqs), (it, threads, chunk, data)
+            assert list(pr.read_len) == [len(s) for s in seqs], (it, threads, chunk, data)
+            for i, s in enumerate(seqs):
+                assert pr.unpack(i) == bytes(b"ACTG"[(c >> 1) & 3] for c in s), (it, i, threads, chunk)
+
+
+def test_parallel_parse_of_structured_files(tmp_path):
+    """Well-formed-looking FASTA/FASTQ (multi-line records, CRLF, quality lines that begin with '@', '>' or '+',
+    empty records) cut into ranges at every granularity: the multi-range parse equals the oracle reader."""
+    rng = np.random.default_rng(12)
+    qual_alpha = np.frombuffer(b"@>+!I5#", dtype=np.uint8)
+    base_alpha = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
+    for it in range(40):
+        fastq, crlf, wrap = bool(it % 2), bool(it % 3 == 0), int(rng.integers(0, 3))
+        eol = b"\r\n" if crlf else b"\n"
+        out = []
+        for r in range(int(rng.integers(1, 60))):
+            n = int(rng.integers(0, 200))
+            seq = rng.choice(base_alpha, size=n).tobytes()
+            if fastq:
+                q = rng.choice(qual_alpha, size=n).tobytes()
+                out += [b"@r%d some comment" % r, seq, b"+", q]
+            else:
+                w = (0, 60, 7)[wrap]
+                lines = [seq[i:i + w] for i in range(0, n, w)] if w and n else [seq]
+                out += [b">r%d" % r] + lines
+        data = eol.join(out) + (eol if it % 4 else b"")
+        path = tmp_path / f"s{it}.txt"
+        path.write_bytes(data)
+        seqs, _ = oracle.parse_reads(data)
+        for threads, chunk in ((1, None), (8, 64), (5, 9), (16, 1)):
+            if chunk is not None:
+                os.environ["LRB_PARSE_CHUNK"] = str(chunk)
+            try:
+                pr = PackedReads.from_file(str(path), threads=threads)
+            finally:
+                os.environ.pop("LRB_PARSE_CHUNK", None)
+            assert list(pr.read_len) == [len(x) for x in seqs], (it, threads, chunk)
+            for i, x in enumerate(seqs):
+                assert pr.unpack(i) == bytes(b"ACTG"[(c >> 1) & 3] for c in x), (it, i, threads, chunk)
 
 
 def test_ingest_nul_byte_and_missing_file(tmp_path):
