@@ -131,7 +131,7 @@ int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_si
  *                   zeroed together and only ever updated by lrb_dev_search / this call)
  *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
  *   mode bit 2 (4): count through shared memory — each bucket's list is split once more into 2-byte lists per
- *                   2^15-key sub-slice (workspace `sub`, sub_capacity entries, fixed share per sub-slice) whose
+ *                   2^15-key sub-slice (workspace `sub`, sub_capacity entries: a fixed share per sub-slice + 8192) whose
  *                   counters live in one SM's shared memory; a bucket whose key skew overflows a share falls back to
  *                   the L2-atomic kernel.  Same table either way.  Ignored when `sub` is NULL.
  * begin() resets the lists; add() appends the windows of blocks [blk_lo, blk_hi) as one chunk (up to 64 chunks,

@@ -21,14 +21,16 @@
 using namespace lrb;
 
 // ---- host allocation -------------------------------------------------------------------------
-void* lrb_host_alloc(size_t bytes, bool* pinned) {
+void* lrb_host_alloc(size_t bytes, bool* pinned, bool want_pinned) {
     void* p = nullptr;
     if (bytes == 0) bytes = 16;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
-        *pinned = true;
-        return p;
+    if (want_pinned) {
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) {
+            *pinned = true;
+            return p;
+        }
+        cudaGetLastError();  // no device (host-only tests): plain memory; any later device call reports the real error
     }
-    cudaGetLastError();  // no device (host-only tests): plain memory; any later device call reports the real error
     *pinned = false;
     if (posix_memalign(&p, 4096, bytes) != 0) return nullptr;
     return p;
@@ -236,7 +238,7 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             const char* e = getenv("LRB_COUNT_PATH");
             const bool want_smem = e ? !strcmp(e, "smem") : nb >= (1u << 19);
             if (do_count && want_smem && !(e && !strcmp(e, "l2"))) {
-                const size_t sub_cap = std::max<size_t>(cap / 4, 1u << 16);
+                const size_t sub_cap = std::max<size_t>(cap / 4, 1u << 16) + 8192;  // + dump area of overflowing shares
                 if (c->part_sub.reserve(sizeof(uint16_t) * sub_cap) == LRB_OK) {
                     c->part.sub = (uint16_t*)c->part_sub.p;
                     c->part.sub_capacity = sub_cap;

@@ -36,6 +36,6 @@ struct lrb_reads {
     bool exc_pinned = false, exc_ready = false;
 };
 
-// page-locked when a CUDA device is usable, plain aligned memory otherwise (host-only unit tests)
-void* lrb_host_alloc(size_t bytes, bool* pinned);
+// page-locked when asked for and a CUDA device is usable, plain aligned memory otherwise (host-only unit tests)
+void* lrb_host_alloc(size_t bytes, bool* pinned, bool want_pinned = true);
 void lrb_host_free(void* p, bool pinned);

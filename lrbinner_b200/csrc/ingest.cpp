@@ -360,7 +360,15 @@ static void free_reads(lrb_reads* r) {
 
 // builds read_blk / tiles from read_len and allocates codes/valid — zeroed only on request: the packers write every
 // word of every block themselves (in parallel, which also spreads the first-touch page faults over the threads)
-static int build_layout(lrb_reads* r, bool zero = false) {
+// Page-locking costs ~0.5 s per GB (measured, profiles/r01_ingest_timing.log) — more than a one-shot pageable copy of
+// the same bytes — so the file / ASCII constructors use plain memory unless LRB_PIN_READS=1; the layout-only
+// constructor (streams that are filled once and profiled many times) pins.
+static bool pin_reads_default() {
+    const char* e = getenv("LRB_PIN_READS");
+    return e && atoi(e) > 0;
+}
+
+static int build_layout(lrb_reads* r, bool zero = false, bool want_pinned = true) {
     const uint64_t n = r->n_reads;
     r->read_blk = (uint32_t*)malloc(sizeof(uint32_t) * (n + 1));
     if (!r->read_blk) return lrb_set_error(LRB_ENOMEM, "out of memory (read_blk)");
@@ -388,9 +396,9 @@ static int build_layout(lrb_reads* r, bool zero = false) {
             ++t;
         }
     }
-    r->codes = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (2 * blk + 2), &r->pinned);
+    r->codes = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (2 * blk + 2), &r->pinned, want_pinned);
     bool pinned2 = r->pinned;
-    r->valid = r->codes ? (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (blk + 1), &pinned2) : nullptr;
+    r->valid = r->codes ? (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (blk + 1), &pinned2, want_pinned) : nullptr;
     if (!r->codes || !r->valid) return lrb_set_error(LRB_ENOMEM, "out of memory (packed stream, %llu blocks)", (unsigned long long)blk);
     if (pinned2 != r->pinned) {  // keep one allocation kind for both
         lrb_host_free(r->valid, pinned2);
@@ -469,8 +477,8 @@ static int index_valid(lrb_reads* r, int threads) {
     uint64_t total = 0;
     for (auto& f : found) total += f.size() / 2;
     bool p1 = false, p2 = false;
-    r->exc_blk = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (total + 1), &p1);
-    r->exc_valid = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (total + 1), &p2);
+    r->exc_blk = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (total + 1), &p1, r->pinned);
+    r->exc_valid = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (total + 1), &p2, r->pinned);
     if (!r->exc_blk || !r->exc_valid || p1 != p2) {
         lrb_host_free(r->exc_blk, p1);
         lrb_host_free(r->exc_valid, p2);
@@ -536,7 +544,7 @@ extern "C" int lrb_reads_from_file(const char* path, int threads, lrb_reads** ou
                 ++i;
             }
     }
-    int rc = build_layout(r);
+    int rc = build_layout(r, false, pin_reads_default());
     if (rc) { free_reads(r); return rc; }
     const double t3 = now();
     pack_all(r, threads, [&](uint64_t i) { return ptr[i]; });
@@ -562,7 +570,7 @@ extern "C" int lrb_reads_from_ascii(const char* bases, const uint64_t* offsets, 
         if (offsets[i + 1] < offsets[i] || l > 0xFFFFFFFFull) { free_reads(r); return lrb_set_error(LRB_EINVAL, "lrb_reads_from_ascii: bad offsets at read %llu", (unsigned long long)i); }
         r->read_len[i] = (uint32_t)l;
     }
-    int rc = build_layout(r);
+    int rc = build_layout(r, false, pin_reads_default());
     if (rc) { free_reads(r); return rc; }
     pack_all(r, threads, [&](uint64_t i) { return (const unsigned char*)bases + offsets[i]; });
     if ((rc = index_valid(r, threads))) { free_reads(r); return rc; }

@@ -32,6 +32,7 @@
 // caller's stream.  Results are bit-identical to the direct kernels: same windows, same keys, integer sums.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -276,9 +277,9 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
         run1 += c1;
     };
     // all loads of a block are issued back to back (no load depends on another), so a prefetch never stalls
-    auto fetch = [&](uint32_t s, uint32_t& v, uint32_t& pv, BlockWindows& b, uint32_t& rd) {
+    auto fetch = [&](uint32_t s, uint32_t& v, uint32_t& pv, BlockWindows& b, uint32_t& rd, uint32_t& r0v) {
         const uint64_t gb = blk_lo + (uint64_t)s * kPartThreads + tid;
-        v = pv = b.pw = b.w0 = b.w1 = rd = 0;
+        v = pv = b.pw = b.w0 = b.w1 = rd = r0v = 0;
         if (gb < blk_hi) {
             v = __ldg(valid + gb);
             pv = gb ? __ldg(valid + gb - 1) : 0u;
@@ -286,13 +287,13 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
             b.w0 = w.x;
             b.w1 = w.y;
             b.pw = gb ? __ldg(codes + 2 * gb - 1) : 0u;
-            if (WITH_RID) rd = __ldg(blk_read + gb) - __ldg(T.rid0 + step0 + s);
+            if (WITH_RID) { rd = __ldg(blk_read + gb); r0v = __ldg(T.rid0 + step0 + s); }
         }
     };
     BlockWindows b;
-    uint32_t v, pv, rd;
+    uint32_t v, pv, rd, r0v;
     if (s_first < s_end) {
-        fetch(s_first, v, pv, b, rd);
+        fetch(s_first, v, pv, b, rd, r0v);
         if (warp == 0) prelude(s_first, 0);
     }
     __syncthreads();
@@ -300,14 +301,14 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
         const int buf = (int)((s - s_first) & 1u);
         uint32_t* cur = s_cur[buf];
         b.m = window15_mask(pv, v);
-        const uint32_t rds = rd << (shift - 1);
+        const uint32_t rds = (rd - r0v) << (shift - 1);
         for_each_key<FULL>(b, key_lo, key_hi, [&](uint32_t kk) {
             const uint32_t idx = atomicAdd(&cur[(kk >> shift) - bucket0], 1u);
             s_ent[idx] = (kk & lo15) | ((kk >> 1) & hi_mask) | rds;
         });
         __syncthreads();
         if (s + 1 < s_end) {  // next step's inputs travel while this one is copied out
-            fetch(s + 1, v, pv, b, rd);
+            fetch(s + 1, v, pv, b, rd, r0v);
             if (warp == 0) prelude(s + 1, buf ^ 1);
         }
         for (int bk = warp; bk < nb; bk += kPartThreads / 32) {  // each warp copies whole runs: contiguous both sides
@@ -362,7 +363,13 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
 // staged word carries its sub-slice).  List order is irrelevant for counting, so no deterministic layout is needed.
 // Sub lists have a fixed capacity C2 (a multiple of the expected size); a bucket whose keys are skewed enough to
 // overflow one raises overflow2[bucket] and is counted by k_count_keys instead (both kernels look at the flag).
-__global__ void __launch_bounds__(256)
+// fire-and-forget shared-memory increment (plain RED: with hundreds of bins the lanes of a warp rarely collide, so
+// the warp-aggregated form the compiler emits for atomicAdd(p, 1) only adds instructions)
+__device__ __forceinline__ void smem_inc(uint32_t* p) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 3)
 k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int bucket, int n_chunks, int sub_bits,
              uint16_t* __restrict__ sub16, uint32_t C2) {
     __shared__ uint32_t s_stage[kStepSlots];  // (sub << 15) | low 15 key bits, grouped by sub-slice
@@ -389,23 +396,34 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         s_cnt[tid] = 0;
         s_cnt[tid + 256] = 0;
         __syncthreads();
-        // the tile is read twice (count, then rank + place; the second read hits L2) instead of parking 32 entries
-        // per thread in registers across the barriers: 3x the resident warps.  Loads go out eight at a time.
+        // the whole tile goes into registers with one round of loads (32 in flight per thread) and stays there for
+        // both passes: a tile's time is a chain of latencies (load, barrier, reservation atomics, barrier, ...), so
+        // fewer, fatter CTAs beat more resident warps here.  Full tiles (all but the last of a region) run unpredicated.
         const bool full = n_tile == kStepSlots;
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-            uint32_t v[8];
+        uint32_t e[32];
+        if (full) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = (j0 + u) * 256u + tid;
-                v[u] = (full || i < n_tile) ? __ldg(src + i) : 0xFFFFFFFFu;
+            for (int j = 0; j < 32; ++j) e[j] = __ldcs(src + j * 256u + tid);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) smem_inc(&s_cnt[(e[j] >> kSubBits) & sub_mask]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t i = j * 256u + tid;
+                e[j] = i < n_tile ? __ldcs(src + i) : 0xFFFFFFFFu;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (full || (j0 + u) * 256u + tid < n_tile) atomicAdd(&s_cnt[(v[u] >> kSubBits) & sub_mask], 1u);
+            for (int j = 0; j < 32; ++j)
+                if (j * 256u + tid < n_tile) smem_inc(&s_cnt[(e[j] >> kSubBits) & sub_mask]);
         }
         __syncthreads();
-        {   // exclusive scan over the sub-slices (two per thread), reservation in the global lists
+        {   // reservation in the global lists (issued first: its latency hides behind the scan), exclusive scan over
+            // the sub-slices (two per thread).  A share that overflows sends its entries to the dump area behind the
+            // lists (the bucket is then counted by k_count_keys), so the sweep needs no bounds check.
             const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+            ull g0 = 0, g1 = 0;
+            if (c0) g0 = atomicAdd(&meta->cur2[2 * tid], (ull)c0);
+            if (c1) g1 = atomicAdd(&meta->cur2[2 * tid + 1], (ull)c1);
             uint32_t x = c0 + c1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -417,41 +435,36 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             uint32_t base = 0;
             for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
             const uint32_t ex0 = base + x - c0 - c1, ex1 = ex0 + c0;
-            if (c0) {
-                const ull g = atomicAdd(&meta->cur2[2 * tid], (ull)c0);
-                if (g + c0 > C2) meta->overflow2[bucket] = 1u;
-                s_delta[2 * tid] = (2 * tid) * C2 + (uint32_t)g - ex0;
-            }
-            if (c1) {
-                const ull g = atomicAdd(&meta->cur2[2 * tid + 1], (ull)c1);
-                if (g + c1 > C2) meta->overflow2[bucket] = 1u;
-                s_delta[2 * tid + 1] = (2 * tid + 1) * C2 + (uint32_t)g - ex1;
-            }
+            const bool o0 = c0 && g0 + c0 > C2, o1 = c1 && g1 + c1 > C2;
+            if (o0 || o1) meta->overflow2[bucket] = 1u;
+            s_delta[2 * tid] = o0 ? limit : (2 * tid) * C2 + (uint32_t)g0 - ex0;
+            s_delta[2 * tid + 1] = o1 ? limit : (2 * tid + 1) * C2 + (uint32_t)g1 - ex1;
             s_cnt[2 * tid] = ex0;
             s_cnt[2 * tid + 1] = ex1;
         }
         __syncthreads();
-        for (int j0 = 0; j0 < 32; j0 += 8) {
-            uint32_t v[8];
+        const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
+        if (full) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = (j0 + u) * 256u + tid;
-                v[u] = (full || i < n_tile) ? __ldcs(src + i) : 0xFFFFFFFFu;
-            }
+            for (int j = 0; j < 32; ++j) s_stage[atomicAdd(&s_cnt[(e[j] >> kSubBits) & sub_mask], 1u)] = e[j] & stage_mask;
+        } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (full || (j0 + u) * 256u + tid < n_tile) {
-                    const uint32_t sub = (v[u] >> kSubBits) & sub_mask;
-                    const uint32_t idx = atomicAdd(&s_cnt[sub], 1u);
-                    s_stage[idx] = (sub << kSubBits) | (v[u] & ((1u << kSubBits) - 1u));
-                }
-            }
+            for (int j = 0; j < 32; ++j)
+                if (j * 256u + tid < n_tile) s_stage[atomicAdd(&s_cnt[(e[j] >> kSubBits) & sub_mask], 1u)] = e[j] & stage_mask;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < n_tile; i += 256) {
-            const uint32_t r = s_stage[i];
-            const uint32_t pos = s_delta[r >> kSubBits] + i;
-            if (pos < limit) sub16[pos] = (uint16_t)(r & ((1u << kSubBits) - 1u));  // out of range only in an overflowed bucket
+        if (full) {
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t i = j * 256u + tid;
+                const uint32_t r = s_stage[i];
+                sub16[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
+            }
+        } else {
+            for (uint32_t i = tid; i < n_tile; i += 256) {
+                const uint32_t r = s_stage[i];
+                sub16[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
+            }
         }
         __syncthreads();
     }
@@ -557,15 +570,26 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
             if (act && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hbase + cell, (uint32_t)__popc(peers));
         };
         uint32_t i0 = span_beg;
-        for (; i0 + 128u <= span_end; i0 += 128u) {  // full steps: no predicates
+        if (i0 + 128u <= span_end) {  // full steps: no predicates; the entries of step t+1 are fetched while step t gathers
             const uint32_t* src = region + i0 + lane;
-            const uint32_t e0 = __ldcs(src), e1 = __ldcs(src + 32), e2 = __ldcs(src + 64), e3 = __ldcs(src + 96);
-            const uint32_t c0 = table[entry_key(e0, bucket_base, hi_mask2)], c1 = table[entry_key(e1, bucket_base, hi_mask2)],
-                           c2 = table[entry_key(e2, bucket_base, hi_mask2)], c3 = table[entry_key(e3, bucket_base, hi_mask2)];
-            emit(e0, c0, i0 + lane, true);
-            emit(e1, c1, i0 + lane + 32u, true);
-            emit(e2, c2, i0 + lane + 64u, true);
-            emit(e3, c3, i0 + lane + 96u, true);
+            uint32_t e0 = __ldcs(src), e1 = __ldcs(src + 32), e2 = __ldcs(src + 64), e3 = __ldcs(src + 96);
+            for (;;) {
+                const uint32_t c0 = table[entry_key(e0, bucket_base, hi_mask2)], c1 = table[entry_key(e1, bucket_base, hi_mask2)],
+                               c2 = table[entry_key(e2, bucket_base, hi_mask2)], c3 = table[entry_key(e3, bucket_base, hi_mask2)];
+                const bool more = i0 + 256u <= span_end;  // warp-uniform
+                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                if (more) {
+                    const uint32_t* nsrc = region + i0 + 128u + lane;
+                    n0 = __ldcs(nsrc); n1 = __ldcs(nsrc + 32); n2 = __ldcs(nsrc + 64); n3 = __ldcs(nsrc + 96);
+                }
+                emit(e0, c0, i0 + lane, true);
+                emit(e1, c1, i0 + lane + 32u, true);
+                emit(e2, c2, i0 + lane + 64u, true);
+                emit(e3, c3, i0 + lane + 96u, true);
+                i0 += 128u;
+                if (!more) break;
+                e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+            }
         }
         if (i0 < span_end) {  // tail of the span
             uint32_t e[4], cnt[4];
@@ -729,8 +753,10 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const bool do_count = mode & 1, do_search = mode & 2;
     // second-level (shared-memory) counting needs the sub-list workspace; without it the L2-atomic kernel does the job
     const int sub_bits = part->shift - 16;
-    uint64_t C2 = (part->sub && sub_bits >= 0) ? ((part->sub_capacity >> sub_bits) & ~7ull) : 0;
-    if (C2 << sub_bits >= (1ull << 32)) C2 = (((1ull << 32) - 8) >> sub_bits) & ~7ull;
+    // the last kStepSlots entries of the workspace are the dump area of overflowing shares
+    uint64_t C2 = (part->sub && sub_bits >= 0 && part->sub_capacity > (uint64_t)kStepSlots)
+                      ? (((part->sub_capacity - kStepSlots) >> sub_bits) & ~7ull) : 0;
+    if ((C2 << sub_bits) + kStepSlots >= (1ull << 32)) C2 = (((1ull << 32) - 8 - kStepSlots) >> sub_bits) & ~7ull;
     const bool smem_count = do_count && (mode & 4) && C2 >= 64;
     if (do_search) {
         if (!hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: search needs hist and sums");
@@ -756,8 +782,11 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const uint32_t hi_mask2 = ((1u << shift) - 1u) & ~0xFFFFu;
     const unsigned grid = (unsigned)sms() * 8;
     const unsigned sgrid = (unsigned)std::min<uint64_t>(grid, (n_tasks + 7) / 8 + 1);  // 8 warps (tasks) per CTA
-    const bool use_lut = ((uint64_t)bins + 1) * S32 < kBinLut;
-    const unsigned grid2 = (unsigned)sms() * 5;
+    // bin rule through a shared-memory table instead of arithmetic: measured slower on B200 (the extra LDS competes with
+    // the gathers for the memory pipe), kept behind LRB_SEARCH_LUT=1 for experiments
+    const char* lut_env = getenv("LRB_SEARCH_LUT");
+    const bool use_lut = lut_env && atoi(lut_env) > 0 && ((uint64_t)bins + 1) * S32 < kBinLut;
+    const unsigned grid2 = (unsigned)sms() * 3;
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
     if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
     for (int b = 0; b < part->n_buckets; ++b) {

@@ -279,7 +279,7 @@ class PartitionWorkspace:
         self.capacity = int(capacity if capacity is not None else max(dr.n_blocks * 32, 1))
         self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
         # second-level lists of the shared-memory count (2 B per entry of ONE bucket at a time, with headroom)
-        self.sub_capacity = int(sub_capacity if sub_capacity is not None else max(self.capacity // 4, 1 << 16))
+        self.sub_capacity = int(sub_capacity if sub_capacity is not None else max(self.capacity // 4, 1 << 16) + 8192)
         self.sub = torch.empty(self.sub_capacity, dtype=torch.int16, device=dr.device) if self.sub_capacity else None
         self.small = torch.zeros(_lib.PART_SMALL_U64, dtype=torch.int64, device=dr.device)
         self.step_capacity = int(lib.lrb_partition_step_capacity(dr.n_blocks, max_chunks))

@@ -367,7 +367,7 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
         table_p = z(2 ** 30)
         dev_table15_partitioned(dr, ws, table_p, True, **kw)
         assert torch.equal(table_p, table_d), kw
-    tiny = PartitionWorkspace(dr, sub_capacity=1 << 14)   # 64 entries per sub-slice list: most overflow
+    tiny = PartitionWorkspace(dr, sub_capacity=(1 << 14) + 8192)   # 64 entries per sub-slice list: most overflow
     table_p = torch.full((2 ** 30,), 7, dtype=torch.int32, device=DEV)
     dev_table15_partitioned(dr, tiny, table_p, True)
     dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=25)
