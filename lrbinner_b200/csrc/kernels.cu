@@ -41,19 +41,26 @@ __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) { return __ldg(p);
 // ------------------------------------------------------------------------------------------------
 // composition: count_kmers (count-kmers.cpp:66-95)
 // ------------------------------------------------------------------------------------------------
+// fire-and-forget shared-memory increment (plain RED; see partition.cu)
+__device__ __forceinline__ void smem_inc(uint32_t* p) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+}
+
+// Per-warp histogram of the RAW k-mers (4^K bins) — one shared-memory RED per base, no LUT lookup in the inner loop;
+// the canonical fold (index of min(x, rc x), count-kmers.cpp:38-64) happens once per tile at flush time.
 template <int K>
 __global__ void __launch_bounds__(kCtaThreads)
 k_composition(lrb_reads_view R, uint32_t* __restrict__ out, uint64_t tile_lo, uint64_t tile_hi) {
     constexpr int P = CompTraits<K>::P;
     constexpr int NK = 1 << (2 * K);
     __shared__ uint16_t s_lut[NK];
-    __shared__ uint32_t s_hist[kWarpsPerCta][P];
+    __shared__ uint32_t s_raw[kWarpsPerCta][NK];
 
     const uint16_t* glut = (K == 3) ? g_lut3 : (K == 4) ? g_lut4 : g_lut5;
     for (int i = threadIdx.x; i < NK; i += kCtaThreads) s_lut[i] = glut[i];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* hist = s_hist[warp];
-    for (int i = lane; i < P; i += 32) hist[i] = 0;
+    uint32_t* raw = s_raw[warp];
+    for (int i = lane; i < NK; i += 32) raw[i] = 0;
     __syncthreads();
 
     const uint64_t tile = tile_lo + (uint64_t)blockIdx.x * kWarpsPerCta + warp;
@@ -71,13 +78,16 @@ k_composition(lrb_reads_view R, uint32_t* __restrict__ out, uint64_t tile_lo, ui
         const uint32_t p0 = (gb - rb0) * 32u;            // read position of slot 0 of this block
         const uint32_t pw = (p0 != 0) ? ld_stream_u32(R.codes + 2 * (size_t)gb - 1) : 0u;
         const uint32_t m = comp_block_mask(p0, len, K);
-        comp_block<K>(pw, w.x, w.y, m, [&](uint32_t kmer) { atomicAdd(&hist[s_lut[kmer]], 1u); });
+        if (K == 3) comp_block<K>(pw, w.x, w.y, m, [&](uint32_t kmer) { atomicAdd(&raw[kmer], 1u); });  // 64 bins: lanes collide, aggregated form
+        else comp_block<K>(pw, w.x, w.y, m, [&](uint32_t kmer) { smem_inc(&raw[kmer]); });
     }
     __syncwarp();
     uint32_t* row = out + (size_t)r * P;
-    for (int i = lane; i < P; i += 32) {
-        const uint32_t c = hist[i];
-        if (c) atomicAdd(row + i, c);
+    for (int i = lane; i < NK; i += 32) {   // fold x and rc(x) into the canonical bin; x < rc(x) owns the pair
+        const uint32_t rc = rc_small((uint32_t)i, K);
+        if ((uint32_t)i > rc) continue;
+        const uint32_t c = raw[i] + (((uint32_t)i != rc) ? raw[rc] : 0u);
+        if (c) atomicAdd(row + s_lut[i], c);
     }
 }
 

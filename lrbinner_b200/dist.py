@@ -286,8 +286,8 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
             "e2e": {"value": L / e2e_ms / 1e6, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "note": "per-rank bytes; max-over-ranks time"},
             "gpu_launches": launches,
-            "roofline": {"kernel": "k_count15 (rank 0)", "bound": "hbm", "achieved": alg / max(count_ms, 1e-6) / 1e6 / 1.0 if count_ms else None,
+            "roofline": {"kernel": "count phase on rank 0 (partition + k2_partition + k_count_smem per bucket)", "bound": "hbm", "achieved": alg / max(count_ms, 1e-6) / 1e6 / 1.0 if count_ms else None,
                          "peak": hbm_peak, "unit": "GB/s", "frac": (alg / max(count_ms, 1e-6) / 1e6) / hbm_peak if count_ms else None,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": count_ms, "includes": "4 GiB table memset"},
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": count_ms, "includes": "4 GiB table memset and the key partition of this rank's rectangle"},
             "phases_ms_rank0": phases, "clocks": clocks, "cpu_baseline": None}
     return line
