@@ -358,31 +358,59 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
 // RED.ADD into an L2-resident slice tops out near 1.3 cycles per lane per SM (~196 G/s on this part,
 // profiles/r01_ubench_roofline.jsonl); shared-memory atomics run ~8x faster.  So for counting, a bucket's list is
 // partitioned once more by the next key bits into sub-slices of 2^15 keys whose counters fit one SM's shared memory.
-// k2_partition: tiles of 8192 entries; per tile count per sub-slice (smem atomics), reserve the tile's share of each
-// sub list with one global atomic per (tile, sub), rank + place into a staging array, sweep it out linearly (the
-// staged word carries its sub-slice).  List order is irrelevant for counting, so no deterministic layout is needed.
-// Sub lists have a fixed capacity C2 (a multiple of the expected size); a bucket whose keys are skewed enough to
-// overflow one raises overflow2[bucket] and is counted by k_count_keys instead (both kernels look at the flag).
+//
+// k2_partition: persistent CTAs take tiles of 8192 entries round-robin.  The tile arrives in shared memory through
+// cp.async while the previous one is processed (double buffer); per tile: count per sub-slice (smem REDs), scan,
+// rank + place into a staging array, linear sweep out (the staged word carries its sub-slice).  Every CTA appends to
+// its OWN segment of every sub-slice list ([sub][cta][C3] entries, cursors in shared memory), so there is no global
+// reservation and no ordering between CTAs; list order is irrelevant for counting.  Segments have a fixed capacity (a
+// multiple of the expected fill); a bucket whose keys are skewed enough to overflow one raises overflow2[bucket] and
+// is counted by k_count_keys instead (both kernels look at the flag); its stray entries go to a dump area.
+// Workspace layout (u16 units): [nsub * n_cta * 2] segment lengths as u32, then the segments, then the dump area.
+constexpr int kL2Threads = 256;
+
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // fire-and-forget shared-memory increment (plain RED: with hundreds of bins the lanes of a warp rarely collide, so
 // the warp-aggregated form the compiler emits for atomicAdd(p, 1) only adds instructions)
 __device__ __forceinline__ void smem_inc(uint32_t* p) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 3)
+struct L2Layout {
+    uint32_t nsub, n_cta, C3;   // sub-slices, CTAs of k2_partition, entries per segment
+    uint64_t seg0, dump;        // first segment / dump area, in u16 units from the start of the workspace
+};
+
+__global__ void __launch_bounds__(kL2Threads, 2)
 k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int bucket, int n_chunks, int sub_bits,
-             uint16_t* __restrict__ sub16, uint32_t C2) {
-    __shared__ uint32_t s_stage[kStepSlots];  // (sub << 15) | low 15 key bits, grouped by sub-slice
-    __shared__ uint32_t s_cnt[kMaxSubs];      // count, then staging cursor
-    __shared__ uint32_t s_delta[kMaxSubs];    // list position of staged position i of sub-slice s = i + s_delta[s]
-    __shared__ uint32_t s_wsum[8];
-    if (meta->overflow) return;
+             uint16_t* __restrict__ ws, L2Layout Y) {
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t* s_tile = s_dyn;                      // [2][kStepSlots]  tile double buffer
+    uint32_t* s_stage = s_dyn + 2 * kStepSlots;    // [kStepSlots]     (sub << 15) | low 15 key bits, grouped by sub-slice
+    __shared__ uint32_t s_cnt[kMaxSubs];           // entries of the tile per sub-slice (zero between tiles)
+    __shared__ uint32_t s_cur[kMaxSubs];           // staging cursor
+    __shared__ uint32_t s_delta[kMaxSubs];         // list position (u16 units from the first segment) of staged position i = i + s_delta
+    __shared__ uint32_t s_fill[kMaxSubs];          // entries this CTA has appended to its segment of each sub-slice
+    __shared__ uint32_t s_wsum[kL2Threads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t nsub = 1u << sub_bits, sub_mask = nsub - 1u;
-    const uint32_t limit = nsub * C2;
+    const uint32_t nsub = Y.nsub, sub_mask = nsub - 1u;
+    uint32_t* seg_len = reinterpret_cast<uint32_t*>(ws);
+    uint16_t* lists = ws + Y.seg0;
+    const uint32_t dump_delta = (uint32_t)(Y.dump - Y.seg0);
+    for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) { s_cnt[i] = 0; s_fill[i] = 0; }
+    if (meta->overflow) {  // lists incomplete: nothing is applied anywhere
+        for (uint32_t i = tid; i < nsub; i += kL2Threads) seg_len[(size_t)i * Y.n_cta + blockIdx.x] = 0;
+        return;
+    }
+    // tiles of the bucket, numbered across the chunk regions
     uint64_t total_tiles = 0;
     for (int c = 0; c < n_chunks; ++c) total_tiles += (meta->counts[c][bucket] + kStepSlots - 1) / kStepSlots;
-    for (uint64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    auto locate = [&](uint64_t tile, const uint32_t*& src, uint32_t& n_tile) {
         int c = 0;
         uint64_t t = tile;
         for (;; ++c) {
@@ -391,39 +419,42 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             t -= tc;
         }
         const uint64_t n_reg = meta->counts[c][bucket];
-        const uint32_t n_tile = (uint32_t)min((uint64_t)kStepSlots, n_reg - t * kStepSlots);
-        const uint32_t* __restrict__ src = ents + meta->offsets[c][bucket] + t * kStepSlots;
-        s_cnt[tid] = 0;
-        s_cnt[tid + 256] = 0;
-        __syncthreads();
-        // the whole tile goes into registers with one round of loads (32 in flight per thread) and stays there for
-        // both passes: a tile's time is a chain of latencies (load, barrier, reservation atomics, barrier, ...), so
-        // fewer, fatter CTAs beat more resident warps here.  Full tiles (all but the last of a region) run unpredicated.
-        const bool full = n_tile == kStepSlots;
-        uint32_t e[32];
+        n_tile = (uint32_t)min((uint64_t)kStepSlots, n_reg - t * kStepSlots);
+        src = ents + meta->offsets[c][bucket] + t * kStepSlots;
+    };
+    auto issue = [&](uint64_t tile, int buf, uint32_t& n_tile) {
+        const uint32_t* src;
+        locate(tile, src, n_tile);
+        uint32_t* dst = s_tile + buf * kStepSlots;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t i = j * (uint32_t)kL2Threads + tid;
+            if (i < n_tile) cp_async4(dst + i, src + i);
+        }
+        cp_async_commit();
+    };
+    uint64_t tile = blockIdx.x;
+    uint32_t n_cur = 0, n_next = 0;
+    if (tile < total_tiles) issue(tile, 0, n_cur);
+    bool ovf = false;
+    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint64_t nxt = tile + gridDim.x;
+        if (nxt < total_tiles) { issue(nxt, buf ^ 1, n_next); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();  // the tile has landed for every thread; the previous sweep is over
+        const uint32_t* tile_e = s_tile + buf * kStepSlots;
+        const bool full = n_cur == kStepSlots;
         if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) e[j] = __ldcs(src + j * 256u + tid);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) smem_inc(&s_cnt[(e[j] >> kSubBits) & sub_mask]);
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) smem_inc(&s_cnt[(tile_e[j * kL2Threads + tid] >> kSubBits) & sub_mask]);
         } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t i = j * 256u + tid;
-                e[j] = i < n_tile ? __ldcs(src + i) : 0xFFFFFFFFu;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j * 256u + tid < n_tile) smem_inc(&s_cnt[(e[j] >> kSubBits) & sub_mask]);
+            for (uint32_t i = tid; i < n_cur; i += kL2Threads) smem_inc(&s_cnt[(tile_e[i] >> kSubBits) & sub_mask]);
         }
         __syncthreads();
-        {   // reservation in the global lists (issued first: its latency hides behind the scan), exclusive scan over
-            // the sub-slices (two per thread).  A share that overflows sends its entries to the dump area behind the
-            // lists (the bucket is then counted by k_count_keys), so the sweep needs no bounds check.
+        {   // exclusive scan over the sub-slices (two per thread); append position in this CTA's segments
             const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
-            ull g0 = 0, g1 = 0;
-            if (c0) g0 = atomicAdd(&meta->cur2[2 * tid], (ull)c0);
-            if (c1) g1 = atomicAdd(&meta->cur2[2 * tid + 1], (ull)c1);
+            s_cnt[2 * tid] = 0;
+            s_cnt[2 * tid + 1] = 0;
             uint32_t x = c0 + c1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -435,72 +466,87 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             uint32_t base = 0;
             for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
             const uint32_t ex0 = base + x - c0 - c1, ex1 = ex0 + c0;
-            const bool o0 = c0 && g0 + c0 > C2, o1 = c1 && g1 + c1 > C2;
-            if (o0 || o1) meta->overflow2[bucket] = 1u;
-            s_delta[2 * tid] = o0 ? limit : (2 * tid) * C2 + (uint32_t)g0 - ex0;
-            s_delta[2 * tid + 1] = o1 ? limit : (2 * tid + 1) * C2 + (uint32_t)g1 - ex1;
-            s_cnt[2 * tid] = ex0;
-            s_cnt[2 * tid + 1] = ex1;
+            const uint32_t f0 = s_fill[2 * tid], f1 = s_fill[2 * tid + 1];
+            const bool o0 = f0 + c0 > Y.C3, o1 = f1 + c1 > Y.C3;
+            ovf |= o0 | o1;
+            // segment of (sub, this CTA) starts at (sub * n_cta + cta) * C3
+            s_delta[2 * tid] = o0 ? dump_delta : ((2 * tid) * Y.n_cta + blockIdx.x) * Y.C3 + f0 - ex0;
+            s_delta[2 * tid + 1] = o1 ? dump_delta : ((2 * tid + 1) * Y.n_cta + blockIdx.x) * Y.C3 + f1 - ex1;
+            s_fill[2 * tid] = o0 ? f0 : f0 + c0;
+            s_fill[2 * tid + 1] = o1 ? f1 : f1 + c1;
+            s_cur[2 * tid] = ex0;
+            s_cur[2 * tid + 1] = ex1;
         }
         __syncthreads();
         const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
         if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s_stage[atomicAdd(&s_cnt[(e[j] >> kSubBits) & sub_mask], 1u)] = e[j] & stage_mask;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t e = tile_e[j * kL2Threads + tid];
+                s_stage[atomicAdd(&s_cur[(e >> kSubBits) & sub_mask], 1u)] = e & stage_mask;
+            }
         } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j * 256u + tid < n_tile) s_stage[atomicAdd(&s_cnt[(e[j] >> kSubBits) & sub_mask], 1u)] = e[j] & stage_mask;
+            for (uint32_t i = tid; i < n_cur; i += kL2Threads) {
+                const uint32_t e = tile_e[i];
+                s_stage[atomicAdd(&s_cur[(e >> kSubBits) & sub_mask], 1u)] = e & stage_mask;
+            }
         }
         __syncthreads();
         if (full) {
 #pragma unroll 8
             for (int j = 0; j < 32; ++j) {
-                const uint32_t i = j * 256u + tid;
+                const uint32_t i = j * kL2Threads + tid;
                 const uint32_t r = s_stage[i];
-                sub16[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
+                lists[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
             }
         } else {
-            for (uint32_t i = tid; i < n_tile; i += 256) {
+            for (uint32_t i = tid; i < n_cur; i += kL2Threads) {
                 const uint32_t r = s_stage[i];
-                sub16[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
+                lists[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
             }
         }
-        __syncthreads();
+        n_cur = n_next;
     }
+    __syncthreads();
+    if (ovf) meta->overflow2[bucket] = 1u;
+    for (uint32_t i = tid; i < nsub; i += kL2Threads) seg_len[(size_t)i * Y.n_cta + blockIdx.x] = s_fill[i];
 }
 
-// one CTA per sub-slice: its list -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
+// one CTA per sub-slice: its segments -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
 __global__ void __launch_bounds__(1024)
-k_count_smem(const uint16_t* __restrict__ sub16, PartMeta* __restrict__ meta, int bucket, uint32_t C2, uint32_t bucket_base,
+k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta, int bucket, L2Layout Y, uint32_t bucket_base,
              uint32_t* __restrict__ table) {
     extern __shared__ uint32_t s_tab[];  // 2^15
-    const uint32_t tid = threadIdx.x, sub = blockIdx.x;
-    const bool skip = meta->overflow || meta->overflow2[bucket];
-    const uint64_t n = meta->cur2[sub];
-    __syncthreads();
-    if (tid == 0) meta->cur2[sub] = 0;  // ready for the next bucket's k2_partition
-    if (skip || n == 0) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, sub = blockIdx.x;
+    if (meta->overflow || meta->overflow2[bucket]) return;
+    const uint32_t* __restrict__ seg_len = reinterpret_cast<const uint32_t*>(ws) + (size_t)sub * Y.n_cta;
     uint4* tab4 = reinterpret_cast<uint4*>(s_tab);
     for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) tab4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const uint16_t* __restrict__ src = sub16 + (size_t)sub * C2;
-    const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
-    const uint32_t n8 = (uint32_t)(n / 8);
     auto bump8 = [&](const uint4& v) {
         atomicAdd(&s_tab[v.x & 0xFFFFu], 1u); atomicAdd(&s_tab[v.x >> 16], 1u);
         atomicAdd(&s_tab[v.y & 0xFFFFu], 1u); atomicAdd(&s_tab[v.y >> 16], 1u);
         atomicAdd(&s_tab[v.z & 0xFFFFu], 1u); atomicAdd(&s_tab[v.z >> 16], 1u);
         atomicAdd(&s_tab[v.w & 0xFFFFu], 1u); atomicAdd(&s_tab[v.w >> 16], 1u);
     };
-    uint32_t i = tid;
-    for (; i + 3 * 1024 < n8; i += 4 * 1024) {  // four 16-byte loads in flight per thread
-        const uint4 v0 = __ldcs(src4 + i), v1 = __ldcs(src4 + i + 1024), v2 = __ldcs(src4 + i + 2048), v3 = __ldcs(src4 + i + 3072);
-        bump8(v0); bump8(v1); bump8(v2); bump8(v3);
+    // a warp per segment (segments are a few KB each): 16 B vectors, up to four in flight per lane
+    bool any = false;
+    for (uint32_t cta = warp; cta < Y.n_cta; cta += 32) {
+        const uint32_t n = __ldg(seg_len + cta);
+        if (!n) continue;
+        any = true;
+        const uint16_t* __restrict__ src = ws + Y.seg0 + ((size_t)sub * Y.n_cta + cta) * Y.C3;
+        const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
+        const uint32_t n8 = n / 8;
+        uint32_t i = lane;
+        for (; i + 96 < n8; i += 128) {
+            const uint4 v0 = __ldcs(src4 + i), v1 = __ldcs(src4 + i + 32), v2 = __ldcs(src4 + i + 64), v3 = __ldcs(src4 + i + 96);
+            bump8(v0); bump8(v1); bump8(v2); bump8(v3);
+        }
+        for (; i < n8; i += 32) bump8(__ldcs(src4 + i));
+        for (uint32_t k = n8 * 8 + lane; k < n; k += 32) atomicAdd(&s_tab[src[k]], 1u);
     }
-    for (; i < n8; i += 1024) bump8(__ldcs(src4 + i));
-    for (uint32_t k = n8 * 8 + tid; k < n; k += 1024) atomicAdd(&s_tab[src[k]], 1u);
-    __syncthreads();
+    if (!__syncthreads_or(any)) return;  // empty sub-slice: the table slice stays as it is
     uint4* slice4 = reinterpret_cast<uint4*>(table + bucket_base + (sub << 16));
     uint4 t4[8];  // 8192 uint4 per slice, eight per thread: all loads first
 #pragma unroll
@@ -753,11 +799,23 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const bool do_count = mode & 1, do_search = mode & 2;
     // second-level (shared-memory) counting needs the sub-list workspace; without it the L2-atomic kernel does the job
     const int sub_bits = part->shift - 16;
-    // the last kStepSlots entries of the workspace are the dump area of overflowing shares
-    uint64_t C2 = (part->sub && sub_bits >= 0 && part->sub_capacity > (uint64_t)kStepSlots)
-                      ? (((part->sub_capacity - kStepSlots) >> sub_bits) & ~7ull) : 0;
-    if ((C2 << sub_bits) + kStepSlots >= (1ull << 32)) C2 = (((1ull << 32) - 8 - kStepSlots) >> sub_bits) & ~7ull;
-    const bool smem_count = do_count && (mode & 4) && C2 >= 64;
+    // workspace of the second level (u16 units): segment lengths, [sub][cta][C3] segments, dump area of overflowing shares
+    L2Layout Y = {0, 0, 0, 0, 0};
+    // CTAs of k2_partition: two per SM, fewer when a bucket cannot have that many tiles anyway (small inputs keep big segments)
+    const unsigned grid2 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms() * 2,
+                                                            part->capacity / ((uint64_t)kStepSlots * std::max(1, part->n_buckets))));
+    if (part->sub && sub_bits >= 0) {
+        Y.nsub = 1u << sub_bits;
+        Y.n_cta = grid2;
+        Y.seg0 = ((uint64_t)Y.nsub * Y.n_cta * 2 + 7) & ~7ull;
+        const uint64_t segs = (uint64_t)Y.nsub * Y.n_cta;
+        uint64_t C3 = part->sub_capacity > Y.seg0 + kStepSlots ? ((part->sub_capacity - Y.seg0 - kStepSlots) / segs) & ~7ull : 0;
+        if (segs * C3 + kStepSlots >= (1ull << 32)) C3 = ((((1ull << 32) - 8 - kStepSlots) / segs)) & ~7ull;
+        Y.C3 = (uint32_t)C3;
+        Y.dump = Y.seg0 + segs * C3;
+    }
+    const uint64_t C2 = Y.C3;
+    const bool smem_count = do_count && (mode & 4) && C2 >= 8;
     if (do_search) {
         if (!hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: search needs hist and sums");
         if (!part->has_rids) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: partition was built without read ids");
@@ -786,14 +844,17 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     // the gathers for the memory pipe), kept behind LRB_SEARCH_LUT=1 for experiments
     const char* lut_env = getenv("LRB_SEARCH_LUT");
     const bool use_lut = lut_env && atoi(lut_env) > 0 && ((uint64_t)bins + 1) * S32 < kBinLut;
-    const unsigned grid2 = (unsigned)sms() * 3;
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
-    if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
+    constexpr int kSmemL2 = 3 * kStepSlots * (int)sizeof(uint32_t);
+    if (smem_count) {
+        LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
+        LRB_CUDA(cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2));
+    }
     for (int b = 0; b < part->n_buckets; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
         if (smem_count) {
-            k2_partition<<<grid2, 256, 0, st>>>(part->keys, const_cast<PartMeta*>(meta), b, part->n_chunks, sub_bits, part->sub, (uint32_t)C2);
-            k_count_smem<<<1u << sub_bits, 1024, kSmemTable, st>>>(part->sub, const_cast<PartMeta*>(meta), b, (uint32_t)C2, bucket_base, table);
+            k2_partition<<<grid2, kL2Threads, kSmemL2, st>>>(part->keys, const_cast<PartMeta*>(meta), b, part->n_chunks, sub_bits, part->sub, Y);
+            k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, table);
         }
         if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table, smem_count ? 1 : 0);
         if (do_search) {

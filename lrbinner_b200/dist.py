@@ -21,6 +21,8 @@ Composition is read-sharded in all plans.  Each rank returns the rows of its own
 The engine argument does the per-GPU work.  The product engine is CudaEngine (lrb_dev_* kernels); the
 CPU tests inject an oracle-backed engine to check the sharding / collective logic over gloo.
 """
+import os
+
 import numpy as np
 
 TABLE_ENTRIES = 1 << 30
@@ -191,7 +193,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     from ONE community (one global 15-mer table).  Times every plan once, keeps the fastest for the K steps."""
     import torch
     import torch.distributed as dist
-    from .profile import COMP_WIDTH, DeviceReads
+    from .profile import COMP_WIDTH, DeviceReads, dev_fill_valid
     from .synth import SynthSpec
 
     k = cfg["k"]
@@ -242,7 +244,12 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     # e2e: every step also moves this rank's inputs host->device and its result rows device->host
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     dr.download_into(layout)
-    h_codes, h_valid = torch.from_numpy(layout.codes.view(np.int32)), torch.from_numpy(layout.valid.view(np.int32))
+    h_codes = torch.from_numpy(layout.codes.view(np.int32))
+    # validity crosses PCIe as the exception list only (0 entries for pure-ACGT reads); the bitmap is rebuilt on the device
+    layout.index_valid(threads=os.cpu_count() or 8)
+    exc_blk, exc_word = layout.exceptions()
+    h_exc = [pin(torch.from_numpy(a.view(np.int32))).copy_(torch.from_numpy(a.view(np.int32))) for a in (exc_blk, exc_word)]
+    d_exc = [torch.empty(len(exc_blk), dtype=torch.int32, device=dev) for _ in range(2)]
     if best == "readshard_ar":   # only the own shard's blocks are needed on this rank
         lo, hi = own_range(n, world, rank)
         rb = layout.read_blk
@@ -253,7 +260,9 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
 
     def e2e_step():
         dr.codes[2 * b0:2 * b1].copy_(h_codes[2 * b0:2 * b1], non_blocking=True)
-        dr.valid[b0:b1].copy_(h_valid[b0:b1], non_blocking=True)
+        for d, h in zip(d_exc, h_exc):
+            d.copy_(h, non_blocking=True)
+        dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
         r = profile_distributed(eng, k, bs, bc, best, table=table)
         for kk in out_h:
             out_h[kk].copy_(r[kk], non_blocking=True)
@@ -271,7 +280,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     e2e_ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
-    h2d = 4 * (2 * (b1 - b0)) + 4 * (b1 - b0)
+    h2d = 4 * (2 * (b1 - b0)) + 8 * len(exc_blk)
     d2h = sum(int(t.numel()) * 4 for t in out_h.values())
 
     count_ms = phases.get("count", 0.0)

@@ -8,8 +8,8 @@ import json; d=json.load(open('gpurun_out/bench_n1_$cp.json')); print('$cp value
 tail -3 gpurun_out/bench_n1_$cp.err
 done
 
-for spec in k2_partition:6 k_search_keys:70 k_partition:0; do
+for spec in k2_partition:6 k_count_smem:6; do
   kn=${spec%%:*}; skip=${spec##*:}
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $skip -c 1 -f -o gpurun_out/r01i_$kn python tools/prof_step.py --reads 1000000 --steps 1 > gpurun_out/ncu_$kn.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $skip -c 1 -f -o gpurun_out/r01k_$kn python tools/prof_step.py --reads 1000000 --steps 1 > gpurun_out/ncu_$kn.log 2>&1
   echo "ncu $kn rc=$?"
 done
