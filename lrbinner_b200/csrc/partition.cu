@@ -367,7 +367,8 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
 // multiple of the expected fill); a bucket whose keys are skewed enough to overflow one raises overflow2[bucket] and
 // is counted by k_count_keys instead (both kernels look at the flag); its stray entries go to a dump area.
 // Workspace layout (u16 units): [nsub * n_cta * 2] segment lengths as u32, then the segments, then the dump area.
-constexpr int kL2Threads = 256;
+constexpr int kL2Threads = 512;   // 16 entries per thread: twice the warps of the 256-thread shape at the same shared-memory footprint
+constexpr int kL2PerThread = kStepSlots / kL2Threads;
 
 __device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -426,8 +427,8 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         const uint32_t* src;
         locate(tile, src, n_tile);
         uint32_t* dst = s_tile + buf * kStepSlots;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
+#pragma unroll
+        for (int j = 0; j < kL2PerThread; ++j) {
             const uint32_t i = j * (uint32_t)kL2Threads + tid;
             if (i < n_tile) cp_async4(dst + i, src + i);
         }
@@ -445,17 +446,16 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         const uint32_t* tile_e = s_tile + buf * kStepSlots;
         const bool full = n_cur == kStepSlots;
         if (full) {
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) smem_inc(&s_cnt[(tile_e[j * kL2Threads + tid] >> kSubBits) & sub_mask]);
+#pragma unroll
+            for (int j = 0; j < kL2PerThread; ++j) smem_inc(&s_cnt[(tile_e[j * kL2Threads + tid] >> kSubBits) & sub_mask]);
         } else {
             for (uint32_t i = tid; i < n_cur; i += kL2Threads) smem_inc(&s_cnt[(tile_e[i] >> kSubBits) & sub_mask]);
         }
         __syncthreads();
-        {   // exclusive scan over the sub-slices (two per thread); append position in this CTA's segments
-            const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
-            s_cnt[2 * tid] = 0;
-            s_cnt[2 * tid + 1] = 0;
-            uint32_t x = c0 + c1;
+        {   // exclusive scan over the sub-slices (one per thread); append position in this CTA's segments
+            const uint32_t c0 = s_cnt[tid];
+            s_cnt[tid] = 0;
+            uint32_t x = c0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
@@ -465,23 +465,20 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             __syncthreads();
             uint32_t base = 0;
             for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
-            const uint32_t ex0 = base + x - c0 - c1, ex1 = ex0 + c0;
-            const uint32_t f0 = s_fill[2 * tid], f1 = s_fill[2 * tid + 1];
-            const bool o0 = f0 + c0 > Y.C3, o1 = f1 + c1 > Y.C3;
-            ovf |= o0 | o1;
+            const uint32_t ex0 = base + x - c0;
+            const uint32_t f0 = s_fill[tid];
+            const bool o0 = f0 + c0 > Y.C3;
+            ovf |= o0;
             // segment of (sub, this CTA) starts at (sub * n_cta + cta) * C3
-            s_delta[2 * tid] = o0 ? dump_delta : ((2 * tid) * Y.n_cta + blockIdx.x) * Y.C3 + f0 - ex0;
-            s_delta[2 * tid + 1] = o1 ? dump_delta : ((2 * tid + 1) * Y.n_cta + blockIdx.x) * Y.C3 + f1 - ex1;
-            s_fill[2 * tid] = o0 ? f0 : f0 + c0;
-            s_fill[2 * tid + 1] = o1 ? f1 : f1 + c1;
-            s_cur[2 * tid] = ex0;
-            s_cur[2 * tid + 1] = ex1;
+            s_delta[tid] = o0 ? dump_delta : (tid * Y.n_cta + blockIdx.x) * Y.C3 + f0 - ex0;
+            s_fill[tid] = o0 ? f0 : f0 + c0;
+            s_cur[tid] = ex0;
         }
         __syncthreads();
         const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
         if (full) {
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
+#pragma unroll
+            for (int j = 0; j < kL2PerThread; ++j) {
                 const uint32_t e = tile_e[j * kL2Threads + tid];
                 s_stage[atomicAdd(&s_cur[(e >> kSubBits) & sub_mask], 1u)] = e & stage_mask;
             }
@@ -493,8 +490,8 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         }
         __syncthreads();
         if (full) {
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) {
+#pragma unroll
+            for (int j = 0; j < kL2PerThread; ++j) {
                 const uint32_t i = j * kL2Threads + tid;
                 const uint32_t r = s_stage[i];
                 lists[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
@@ -508,7 +505,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         n_cur = n_next;
     }
     __syncthreads();
-    if (ovf) meta->overflow2[bucket] = 1u;
+    if (__syncthreads_or(ovf)) { if (tid == 0) meta->overflow2[bucket] = 1u; }
     for (uint32_t i = tid; i < nsub; i += kL2Threads) seg_len[(size_t)i * Y.n_cta + blockIdx.x] = s_fill[i];
 }
 
@@ -529,22 +526,37 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
         atomicAdd(&s_tab[v.z & 0xFFFFu], 1u); atomicAdd(&s_tab[v.z >> 16], 1u);
         atomicAdd(&s_tab[v.w & 0xFFFFu], 1u); atomicAdd(&s_tab[v.w >> 16], 1u);
     };
-    // a warp per segment (segments are a few KB each): 16 B vectors, up to four in flight per lane
-    bool any = false;
-    for (uint32_t cta = warp; cta < Y.n_cta; cta += 32) {
-        const uint32_t n = __ldg(seg_len + cta);
-        if (!n) continue;
-        any = true;
-        const uint16_t* __restrict__ src = ws + Y.seg0 + ((size_t)sub * Y.n_cta + cta) * Y.C3;
-        const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
+    // a warp per segment (a few KB each), 16 B vectors.  The lengths of the warp's segments are fetched in one go and
+    // the first four vectors of the next segment travel while the current one is counted.
+    const uint32_t my_cta = warp + 32u * lane;                     // lane l holds the length of the warp's l-th segment
+    const uint32_t my_len = my_cta < Y.n_cta ? __ldg(seg_len + my_cta) : 0u;
+    const uint32_t n_seg = (Y.n_cta > warp) ? (Y.n_cta - warp + 31u) / 32u : 0u;   // segments of this warp (<= 32 per round)
+    bool any = __any_sync(0xFFFFFFFFu, my_len != 0u);
+    auto seg_ptr = [&](uint32_t k) { return ws + Y.seg0 + ((size_t)sub * Y.n_cta + (warp + 32u * k)) * Y.C3; };
+    auto fetch4 = [&](uint32_t k, uint32_t n, uint4* v) {
+        const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(seg_ptr(k));
         const uint32_t n8 = n / 8;
-        uint32_t i = lane;
-        for (; i + 96 < n8; i += 128) {
-            const uint4 v0 = __ldcs(src4 + i), v1 = __ldcs(src4 + i + 32), v2 = __ldcs(src4 + i + 64), v3 = __ldcs(src4 + i + 96);
-            bump8(v0); bump8(v1); bump8(v2); bump8(v3);
-        }
-        for (; i < n8; i += 32) bump8(__ldcs(src4 + i));
-        for (uint32_t k = n8 * 8 + lane; k < n; k += 32) atomicAdd(&s_tab[src[k]], 1u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (lane + 32u * u < n8) ? __ldcs(src4 + lane + 32u * u) : make_uint4(0, 0, 0, 0);
+    };
+    const uint32_t rounds = min(n_seg, 32u);  // n_cta <= 1024 would need a second round of lengths; grids here are <= 2 per SM
+    uint4 cur[4], nxt[4];
+    uint32_t n = rounds ? __shfl_sync(0xFFFFFFFFu, my_len, 0) : 0u;
+    if (rounds) fetch4(0, n, cur);
+    for (uint32_t k = 0; k < rounds; ++k) {
+        const uint32_t n_next = (k + 1 < rounds) ? __shfl_sync(0xFFFFFFFFu, my_len, (k + 1) & 31u) : 0u;
+        if (k + 1 < rounds) fetch4(k + 1, n_next, nxt);
+        const uint32_t n8 = n / 8;
+        const uint16_t* __restrict__ src = seg_ptr(k);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lane + 32u * u < n8) bump8(cur[u]);
+        const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
+        for (uint32_t i = lane + 128u; i < n8; i += 32) bump8(__ldcs(src4 + i));      // long segments: the rest
+        for (uint32_t i = n8 * 8 + lane; i < n; i += 32) atomicAdd(&s_tab[src[i]], 1u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+        n = n_next;
     }
     if (!__syncthreads_or(any)) return;  // empty sub-slice: the table slice stays as it is
     uint4* slice4 = reinterpret_cast<uint4*>(table + bucket_base + (sub << 16));
@@ -568,7 +580,7 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
 constexpr uint32_t kTaskRuns = 16;
 constexpr uint32_t kBinLut = 2048;  // counts below this go through a shared-memory bin table when (B+1)*S fits
 
-template <bool USE_LUT>
+template <bool USE_LUT, int U>
 __global__ void __launch_bounds__(256)
 k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, ChunkList L,
               StepTables T, uint32_t bucket_base, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
@@ -616,26 +628,38 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
             if (act && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(hbase + cell, (uint32_t)__popc(peers));
         };
         uint32_t i0 = span_beg;
-        if (i0 + 128u <= span_end) {  // full steps: no predicates; the entries of step t+1 are fetched while step t gathers
+        constexpr uint32_t kStep = 32u * U;
+        if (i0 + kStep <= span_end) {  // full steps: no predicates; the entries of step t+1 are fetched while step t gathers
+            uint32_t e[U], nx[U], cn[U];
             const uint32_t* src = region + i0 + lane;
-            uint32_t e0 = __ldcs(src), e1 = __ldcs(src + 32), e2 = __ldcs(src + 64), e3 = __ldcs(src + 96);
+#pragma unroll
+            for (int u = 0; u < U; ++u) e[u] = __ldcs(src + 32 * u);
             for (;;) {
-                const uint32_t c0 = table[entry_key(e0, bucket_base, hi_mask2)], c1 = table[entry_key(e1, bucket_base, hi_mask2)],
-                               c2 = table[entry_key(e2, bucket_base, hi_mask2)], c3 = table[entry_key(e3, bucket_base, hi_mask2)];
-                const bool more = i0 + 256u <= span_end;  // warp-uniform
-                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) cn[u] = table[entry_key(e[u], bucket_base, hi_mask2)];
+                const bool more = i0 + 2u * kStep <= span_end;  // warp-uniform
                 if (more) {
-                    const uint32_t* nsrc = region + i0 + 128u + lane;
-                    n0 = __ldcs(nsrc); n1 = __ldcs(nsrc + 32); n2 = __ldcs(nsrc + 64); n3 = __ldcs(nsrc + 96);
+                    const uint32_t* nsrc = region + i0 + kStep + lane;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) nx[u] = __ldcs(nsrc + 32 * u);
                 }
-                emit(e0, c0, i0 + lane, true);
-                emit(e1, c1, i0 + lane + 32u, true);
-                emit(e2, c2, i0 + lane + 64u, true);
-                emit(e3, c3, i0 + lane + 96u, true);
-                i0 += 128u;
+#pragma unroll
+                for (int u = 0; u < U; ++u) emit(e[u], cn[u], i0 + lane + 32u * u, true);
+                i0 += kStep;
                 if (!more) break;
-                e0 = n0; e1 = n1; e2 = n2; e3 = n3;
+#pragma unroll
+                for (int u = 0; u < U; ++u) e[u] = nx[u];
             }
+        }
+        for (; i0 + 128u <= span_end; i0 += 128u) {  // (U > 4) full 128-entry steps that are left
+            const uint32_t* src = region + i0 + lane;
+            const uint32_t e0 = __ldcs(src), e1 = __ldcs(src + 32), e2 = __ldcs(src + 64), e3 = __ldcs(src + 96);
+            const uint32_t c0 = table[entry_key(e0, bucket_base, hi_mask2)], c1 = table[entry_key(e1, bucket_base, hi_mask2)],
+                           c2 = table[entry_key(e2, bucket_base, hi_mask2)], c3 = table[entry_key(e3, bucket_base, hi_mask2)];
+            emit(e0, c0, i0 + lane, true);
+            emit(e1, c1, i0 + lane + 32u, true);
+            emit(e2, c2, i0 + lane + 64u, true);
+            emit(e3, c3, i0 + lane + 96u, true);
         }
         if (i0 < span_end) {  // tail of the span
             uint32_t e[4], cnt[4];
@@ -802,7 +826,7 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     // workspace of the second level (u16 units): segment lengths, [sub][cta][C3] segments, dump area of overflowing shares
     L2Layout Y = {0, 0, 0, 0, 0};
     // CTAs of k2_partition: two per SM, fewer when a bucket cannot have that many tiles anyway (small inputs keep big segments)
-    const unsigned grid2 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms() * 2,
+    const unsigned grid2 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * 2, 1024),
                                                             part->capacity / ((uint64_t)kStepSlots * std::max(1, part->n_buckets))));
     if (part->sub && sub_bits >= 0) {
         Y.nsub = 1u << sub_bits;
@@ -844,6 +868,8 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     // the gathers for the memory pipe), kept behind LRB_SEARCH_LUT=1 for experiments
     const char* lut_env = getenv("LRB_SEARCH_LUT");
     const bool use_lut = lut_env && atoi(lut_env) > 0 && ((uint64_t)bins + 1) * S32 < kBinLut;
+    const char* un_env = getenv("LRB_SEARCH_UNROLL");  // gathers in flight per lane: 4 (default) or 8
+    const bool unroll8 = un_env && atoi(un_env) == 8;
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
     constexpr int kSmemL2 = 3 * kStepSlots * (int)sizeof(uint32_t);
     if (smem_count) {
@@ -858,12 +884,13 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
         }
         if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table, smem_count ? 1 : 0);
         if (do_search) {
-            if (use_lut)
-                k_search_keys<true><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32,
-                                                           magic, (uint32_t)bins, hist);
-            else
-                k_search_keys<false><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32,
-                                                            magic, (uint32_t)bins, hist);
+#define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
+    k_search_keys<LUT, UN><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \
+                                                  (uint32_t)bins, hist)
+            if (use_lut) LRB_LAUNCH_SEARCH(true, 4);
+            else if (unroll8) LRB_LAUNCH_SEARCH(false, 8);
+            else LRB_LAUNCH_SEARCH(false, 4);
+#undef LRB_LAUNCH_SEARCH
         }
     }
     if (do_search && part->n_reads)
