@@ -130,10 +130,10 @@ int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_si
  *                   sums[r] is rewritten as the sum of hist row r for r < n_reads (hist and sums must have been
  *                   zeroed together and only ever updated by lrb_dev_search / this call)
  *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
- *   mode bit 2 (4): count through shared memory — each bucket's list is split once more into 2-byte lists per
- *                   2^15-key sub-slice (workspace `sub`, sub_capacity entries: a fixed share per sub-slice + 8192) whose
- *                   counters live in one SM's shared memory; a bucket whose key skew overflows a share falls back to
- *                   the L2-atomic kernel.  Same table either way.  Ignored when `sub` is NULL.
+ *   mode bit 2 (4): count through shared memory.  When `sub` is given (sub_capacity u16 entries, >= ~1.3 x capacity; 2 x is
+ *                   comfortable) add() also splits every bucket list of the chunk into 2-byte lists per 2^15-key
+ *                   sub-slice, whose counters then live in one SM's shared memory; a bucket whose key skew overflows a
+ *                   list's fixed share falls back to the L2-atomic kernel.  Same table either way.  Ignored without `sub`.
  * begin() resets the lists; add() appends the windows of blocks [blk_lo, blk_hi) as one chunk (up to 64 chunks,
  * e.g. one per host-to-device copy so partitioning overlaps the transfer); build() = begin + one add.  A
  * partition can be applied several times (count, exchange tables between GPUs, then search).  Everything is
@@ -161,6 +161,9 @@ typedef struct {
     int n_buckets, shift, has_rids, n_chunks;
     uint32_t key_lo, key_hi;
     uint32_t chunk_step0[LRB_PART_MAX_CHUNKS], chunk_nsteps[LRB_PART_MAX_CHUNKS];
+    int l2_enabled;                /* second-level lists are being built (filled by begin()) */
+    uint32_t l2_ncta, l2_C3;
+    uint64_t l2_seg0, l2_span;
 } lrb_partition;
 uint64_t lrb_partition_step_capacity(uint64_t n_blocks, int max_chunks);
 uint64_t lrb_partition_steps_words(uint64_t step_capacity);

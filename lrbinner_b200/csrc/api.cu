@@ -238,7 +238,7 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             const char* e = getenv("LRB_COUNT_PATH");
             const bool want_smem = e ? !strcmp(e, "smem") : nb >= (1u << 19);
             if (do_count && want_smem && !(e && !strcmp(e, "l2"))) {
-                const size_t sub_cap = std::max<size_t>(cap / 4, 1u << 16) + 8192;  // + dump area of overflowing shares
+                const size_t sub_cap = 2 * cap + (1u << 22);  // 2-byte entries in fixed-size segments: 2x headroom + fill counters and dump areas
                 if (c->part_sub.reserve(sizeof(uint16_t) * sub_cap) == LRB_OK) {
                     c->part.sub = (uint16_t*)c->part_sub.p;
                     c->part.sub_capacity = sub_cap;

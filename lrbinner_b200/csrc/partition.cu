@@ -61,7 +61,6 @@ struct PartMeta {
     ull chunk_base[kMaxChunks + 1];        // first entry of each chunk's region
     ull needed;                            // entries the chunks added so far need in total
     ull overflow;                          // != 0: capacity exceeded, lists are incomplete (apply does nothing)
-    ull cur2[kMaxSubs];                    // second level: fill cursor of each sub-slice list of the bucket in flight
     uint32_t overflow2[kMaxBuckets];       // second level: a sub list of bucket b overflowed -> k_count_keys counts b
 };
 static_assert(sizeof(PartMeta) <= sizeof(ull) * LRB_PART_SMALL_U64, "lrb_partition.small too small");
@@ -354,20 +353,22 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
     }
 }
 
-// ---- second level (count only): bucket list -> 2-byte lists per 2^15-key sub-slice -> shared-memory counting ------
+// ---- second level (count only): bucket lists -> 2-byte lists per 2^15-key sub-slice -> shared-memory counting ------
 // RED.ADD into an L2-resident slice tops out near 1.3 cycles per lane per SM (~196 G/s on this part,
-// profiles/r01_ubench_roofline.jsonl); shared-memory atomics run ~8x faster.  So for counting, a bucket's list is
+// profiles/r01_ubench_roofline.jsonl); shared-memory atomics run ~8x faster.  So for counting, every bucket's list is
 // partitioned once more by the next key bits into sub-slices of 2^15 keys whose counters fit one SM's shared memory.
 //
-// k2_partition: persistent CTAs take tiles of 8192 entries round-robin.  The tile arrives in shared memory through
-// cp.async while the previous one is processed (double buffer); per tile: count per sub-slice (smem REDs), scan,
-// rank + place into a staging array, linear sweep out (the staged word carries its sub-slice).  Every CTA appends to
-// its OWN segment of every sub-slice list ([sub][cta][C3] entries, cursors in shared memory), so there is no global
-// reservation and no ordering between CTAs; list order is irrelevant for counting.  Segments have a fixed capacity (a
-// multiple of the expected fill); a bucket whose keys are skewed enough to overflow one raises overflow2[bucket] and
-// is counted by k_count_keys instead (both kernels look at the flag); its stray entries go to a dump area.
-// Workspace layout (u16 units): [nsub * n_cta * 2] segment lengths as u32, then the segments, then the dump area.
-constexpr int kL2Threads = 512;   // 16 entries per thread: twice the warps of the 256-thread shape at the same shared-memory footprint
+// k2_partition runs once per chunk, right after k_partition (so in the host pipeline it sits in the shadow of the
+// host-to-device copy of the next chunk): persistent CTAs take tiles of 8192 entries of the chunk's bucket regions
+// round-robin.  The tile arrives in shared memory through cp.async while the previous one is processed (double
+// buffer); per tile: count per sub-slice (smem REDs), scan, rank + place into a staging array, linear sweep out (the
+// staged word carries its sub-slice).  Every CTA appends to its OWN segment of every (bucket, sub-slice) list
+// ([bucket][sub][cta][C3] entries; fill counters in a private global row), so there is no reservation between CTAs
+// and no ordering; list order is irrelevant for counting.  Segments have a fixed capacity (a multiple of the expected
+// fill); a bucket whose keys are skewed enough to overflow one raises overflow2[bucket] and is counted by
+// k_count_keys instead (both count kernels look at the flag); its stray entries go to the bucket's dump area.
+// Workspace (u16 units): fill[n_cta][n_buckets * nsub] as u32, then per bucket its segments + a dump area.
+constexpr int kL2Threads = 512;   // 16 entries per thread: twice the warps of a 256-thread shape at the same shared-memory footprint
 constexpr int kL2PerThread = kStepSlots / kL2Threads;
 
 __device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
@@ -383,49 +384,54 @@ __device__ __forceinline__ void smem_inc(uint32_t* p) {
 }
 
 struct L2Layout {
-    uint32_t nsub, n_cta, C3;   // sub-slices, CTAs of k2_partition, entries per segment
-    uint64_t seg0, dump;        // first segment / dump area, in u16 units from the start of the workspace
+    uint32_t nsub, n_cta, C3, nb;   // sub-slices per bucket, CTAs of k2_partition, entries per segment, buckets
+    uint64_t seg0, span;            // first segment; u16 units per bucket (its segments + the dump area)
+    __host__ __device__ uint64_t bucket_base(uint32_t b) const { return seg0 + (uint64_t)b * span; }
+    __host__ __device__ uint32_t dump_delta() const { return nsub * n_cta * C3; }  // inside the bucket's span
 };
 
 __global__ void __launch_bounds__(kL2Threads, 2)
-k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int bucket, int n_chunks, int sub_bits,
-             uint16_t* __restrict__ ws, L2Layout Y) {
+k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int c, uint16_t* __restrict__ ws, L2Layout Y) {
     extern __shared__ uint32_t s_dyn[];
     uint32_t* s_tile = s_dyn;                      // [2][kStepSlots]  tile double buffer
     uint32_t* s_stage = s_dyn + 2 * kStepSlots;    // [kStepSlots]     (sub << 15) | low 15 key bits, grouped by sub-slice
     __shared__ uint32_t s_cnt[kMaxSubs];           // entries of the tile per sub-slice (zero between tiles)
     __shared__ uint32_t s_cur[kMaxSubs];           // staging cursor
-    __shared__ uint32_t s_delta[kMaxSubs];         // list position (u16 units from the first segment) of staged position i = i + s_delta
-    __shared__ uint32_t s_fill[kMaxSubs];          // entries this CTA has appended to its segment of each sub-slice
+    __shared__ uint32_t s_delta[kMaxSubs];         // list position (inside the bucket's span) of staged position i = i + s_delta
     __shared__ uint32_t s_wsum[kL2Threads / 32];
+    __shared__ uint32_t s_tiles0[kMaxBuckets + 1]; // first tile of each bucket region of the chunk
+    __shared__ uint32_t s_ovf[kMaxBuckets];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t nsub = Y.nsub, sub_mask = nsub - 1u;
-    uint32_t* seg_len = reinterpret_cast<uint32_t*>(ws);
-    uint16_t* lists = ws + Y.seg0;
-    const uint32_t dump_delta = (uint32_t)(Y.dump - Y.seg0);
-    for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) { s_cnt[i] = 0; s_fill[i] = 0; }
-    if (meta->overflow) {  // lists incomplete: nothing is applied anywhere
-        for (uint32_t i = tid; i < nsub; i += kL2Threads) seg_len[(size_t)i * Y.n_cta + blockIdx.x] = 0;
-        return;
-    }
-    // tiles of the bucket, numbered across the chunk regions
-    uint64_t total_tiles = 0;
-    for (int c = 0; c < n_chunks; ++c) total_tiles += (meta->counts[c][bucket] + kStepSlots - 1) / kStepSlots;
-    auto locate = [&](uint64_t tile, const uint32_t*& src, uint32_t& n_tile) {
-        int c = 0;
-        uint64_t t = tile;
-        for (;; ++c) {
-            const uint64_t tc = (meta->counts[c][bucket] + kStepSlots - 1) / kStepSlots;
-            if (t < tc) break;
-            t -= tc;
+    if (meta->overflow) return;  // lists incomplete: nothing is applied anywhere
+    uint32_t* __restrict__ fill = reinterpret_cast<uint32_t*>(ws) + (size_t)blockIdx.x * Y.nb * nsub;  // this CTA's row
+    for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) s_cnt[i] = 0;
+    if (tid < (uint32_t)kMaxBuckets) s_ovf[tid] = 0;
+    if (tid == 0) {  // tiles of the chunk, numbered across its bucket regions
+        uint32_t acc = 0;
+        for (uint32_t b = 0; b < Y.nb; ++b) {
+            s_tiles0[b] = acc;
+            acc += (uint32_t)((meta->counts[c][b] + kStepSlots - 1) / kStepSlots);
         }
-        const uint64_t n_reg = meta->counts[c][bucket];
-        n_tile = (uint32_t)min((uint64_t)kStepSlots, n_reg - t * kStepSlots);
-        src = ents + meta->offsets[c][bucket] + t * kStepSlots;
+        for (uint32_t b = Y.nb; b <= (uint32_t)kMaxBuckets; ++b) s_tiles0[b] = acc;
+    }
+    __syncthreads();
+    const uint32_t total_tiles = s_tiles0[Y.nb];
+    auto locate = [&](uint32_t tile, uint32_t& b, const uint32_t*& src, uint32_t& n_tile) {
+        uint32_t lo = 0, hi = Y.nb;  // last bucket whose first tile is <= tile
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_tiles0[mid] <= tile) lo = mid; else hi = mid;
+        }
+        b = lo;
+        const uint32_t t = tile - s_tiles0[b];
+        const uint64_t n_reg = meta->counts[c][b];
+        n_tile = (uint32_t)min((uint64_t)kStepSlots, n_reg - (uint64_t)t * kStepSlots);
+        src = ents + meta->offsets[c][b] + (uint64_t)t * kStepSlots;
     };
-    auto issue = [&](uint64_t tile, int buf, uint32_t& n_tile) {
+    auto issue = [&](uint32_t tile, int buf, uint32_t& b, uint32_t& n_tile) {
         const uint32_t* src;
-        locate(tile, src, n_tile);
+        locate(tile, b, src, n_tile);
         uint32_t* dst = s_tile + buf * kStepSlots;
 #pragma unroll
         for (int j = 0; j < kL2PerThread; ++j) {
@@ -434,14 +440,15 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         }
         cp_async_commit();
     };
-    uint64_t tile = blockIdx.x;
-    uint32_t n_cur = 0, n_next = 0;
-    if (tile < total_tiles) issue(tile, 0, n_cur);
-    bool ovf = false;
+    uint32_t tile = blockIdx.x;
+    uint32_t n_cur = 0, n_next = 0, b_cur = 0, b_next = 0;
+    if (tile < total_tiles) issue(tile, 0, b_cur, n_cur);
     for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        const uint64_t nxt = tile + gridDim.x;
-        if (nxt < total_tiles) { issue(nxt, buf ^ 1, n_next); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        const uint32_t nxt = tile + gridDim.x;
+        if (nxt < total_tiles) { issue(nxt, buf ^ 1, b_next, n_next); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        uint32_t* frow = fill + (size_t)b_cur * nsub;
+        const uint32_t f0 = tid < nsub ? frow[tid] : 0u;  // travels while the tile is counted
         __syncthreads();  // the tile has landed for every thread; the previous sweep is over
         const uint32_t* tile_e = s_tile + buf * kStepSlots;
         const bool full = n_cur == kStepSlots;
@@ -466,12 +473,11 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             uint32_t base = 0;
             for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
             const uint32_t ex0 = base + x - c0;
-            const uint32_t f0 = s_fill[tid];
             const bool o0 = f0 + c0 > Y.C3;
-            ovf |= o0;
-            // segment of (sub, this CTA) starts at (sub * n_cta + cta) * C3
-            s_delta[tid] = o0 ? dump_delta : (tid * Y.n_cta + blockIdx.x) * Y.C3 + f0 - ex0;
-            s_fill[tid] = o0 ? f0 : f0 + c0;
+            if (o0) s_ovf[b_cur] = 1u;
+            // segment of (sub, this CTA) starts at (sub * n_cta + cta) * C3 inside the bucket's span
+            s_delta[tid] = o0 ? Y.dump_delta() : (tid * Y.n_cta + blockIdx.x) * Y.C3 + f0 - ex0;
+            if (tid < nsub && c0 && !o0) frow[tid] = f0 + c0;
             s_cur[tid] = ex0;
         }
         __syncthreads();
@@ -489,6 +495,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             }
         }
         __syncthreads();
+        uint16_t* __restrict__ lists = ws + Y.bucket_base(b_cur);
         if (full) {
 #pragma unroll
             for (int j = 0; j < kL2PerThread; ++j) {
@@ -503,10 +510,10 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             }
         }
         n_cur = n_next;
+        b_cur = b_next;
     }
     __syncthreads();
-    if (__syncthreads_or(ovf)) { if (tid == 0) meta->overflow2[bucket] = 1u; }
-    for (uint32_t i = tid; i < nsub; i += kL2Threads) seg_len[(size_t)i * Y.n_cta + blockIdx.x] = s_fill[i];
+    if (tid < Y.nb && s_ovf[tid]) meta->overflow2[tid] = 1u;
 }
 
 // one CTA per sub-slice: its segments -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
@@ -516,7 +523,9 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     extern __shared__ uint32_t s_tab[];  // 2^15
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, sub = blockIdx.x;
     if (meta->overflow || meta->overflow2[bucket]) return;
-    const uint32_t* __restrict__ seg_len = reinterpret_cast<const uint32_t*>(ws) + (size_t)sub * Y.n_cta;
+    const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + sub;  // + cta * nb * nsub
+    const size_t fill_stride = (size_t)Y.nb * Y.nsub;
+    const uint16_t* __restrict__ lists = ws + Y.bucket_base(bucket);
     uint4* tab4 = reinterpret_cast<uint4*>(s_tab);
     for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) tab4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -529,17 +538,17 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     // a warp per segment (a few KB each), 16 B vectors.  The lengths of the warp's segments are fetched in one go and
     // the first four vectors of the next segment travel while the current one is counted.
     const uint32_t my_cta = warp + 32u * lane;                     // lane l holds the length of the warp's l-th segment
-    const uint32_t my_len = my_cta < Y.n_cta ? __ldg(seg_len + my_cta) : 0u;
-    const uint32_t n_seg = (Y.n_cta > warp) ? (Y.n_cta - warp + 31u) / 32u : 0u;   // segments of this warp (<= 32 per round)
+    const uint32_t my_len = my_cta < Y.n_cta ? __ldg(fill + my_cta * fill_stride) : 0u;
+    const uint32_t n_seg = (Y.n_cta > warp) ? (Y.n_cta - warp + 31u) / 32u : 0u;   // segments of this warp (n_cta <= 1024)
     bool any = __any_sync(0xFFFFFFFFu, my_len != 0u);
-    auto seg_ptr = [&](uint32_t k) { return ws + Y.seg0 + ((size_t)sub * Y.n_cta + (warp + 32u * k)) * Y.C3; };
+    auto seg_ptr = [&](uint32_t k) { return lists + ((size_t)sub * Y.n_cta + (warp + 32u * k)) * Y.C3; };
     auto fetch4 = [&](uint32_t k, uint32_t n, uint4* v) {
         const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(seg_ptr(k));
         const uint32_t n8 = n / 8;
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = (lane + 32u * u < n8) ? __ldcs(src4 + lane + 32u * u) : make_uint4(0, 0, 0, 0);
     };
-    const uint32_t rounds = min(n_seg, 32u);  // n_cta <= 1024 would need a second round of lengths; grids here are <= 2 per SM
+    const uint32_t rounds = min(n_seg, 32u);
     uint4 cur[4], nxt[4];
     uint32_t n = rounds ? __shfl_sync(0xFFFFFFFFu, my_len, 0) : 0u;
     if (rounds) fetch4(0, n, cur);
@@ -739,6 +748,29 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
     part->steps_used = 0;
     part->n_reads = 0;
     LRB_CUDA(cudaMemsetAsync(part->small, 0, sizeof(PartMeta), (cudaStream_t)stream));
+    // second-level lists (shared-memory count): built chunk by chunk in add() when the workspace has room for them
+    part->l2_enabled = 0;
+    part->l2_ncta = part->l2_C3 = 0;
+    part->l2_seg0 = part->l2_span = 0;
+    const int sub_bits = shift - 16;
+    if (part->sub && sub_bits >= 0) {
+        const uint64_t nsub = 1ull << sub_bits;
+        // CTAs of k2_partition: two per SM, fewer when the lists cannot have that many tiles anyway (small inputs keep big segments)
+        const uint64_t n_cta = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * 2, 1024), part->capacity / ((uint64_t)kStepSlots * nb)));
+        const uint64_t seg0 = (n_cta * nb * nsub * 2 + 7) & ~7ull;               // fill counters (u32) in u16 units
+        const uint64_t segs = (uint64_t)nb * nsub * n_cta;
+        uint64_t C3 = part->sub_capacity > seg0 + (uint64_t)nb * kStepSlots ? ((part->sub_capacity - seg0 - (uint64_t)nb * kStepSlots) / segs) & ~7ull : 0;
+        if (nsub * n_cta * C3 + kStepSlots >= (1ull << 32)) C3 = ((((1ull << 32) - 8 - kStepSlots) / (nsub * n_cta))) & ~7ull;
+        // worth building only if the segments could hold every window with some slack (else most buckets would fall back)
+        if (C3 >= 8 && segs * C3 >= part->capacity + part->capacity / 4) {
+            part->l2_enabled = 1;
+            part->l2_ncta = (uint32_t)n_cta;
+            part->l2_C3 = (uint32_t)C3;
+            part->l2_seg0 = seg0;
+            part->l2_span = nsub * n_cta * C3 + kStepSlots;
+            LRB_CUDA(cudaMemsetAsync(part->sub, 0, seg0 * sizeof(uint16_t), (cudaStream_t)stream));
+        }
+    }
     return LRB_OK;
 }
 
@@ -776,6 +808,14 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
     if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
     else { if (full) LRB_LAUNCH_PART(false, true); else LRB_LAUNCH_PART(false, false); }
 #undef LRB_LAUNCH_PART
+    if (part->l2_enabled) {
+        L2Layout Y;
+        Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb;
+        Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
+        constexpr int kSmemL2 = 3 * kStepSlots * (int)sizeof(uint32_t);
+        LRB_CUDA(cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2));
+        k2_partition<<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y);
+    }
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -821,25 +861,13 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
                                        uint32_t* hist, uint32_t* sums, void* stream) {
     if (!part || !table) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: null argument");
     const bool do_count = mode & 1, do_search = mode & 2;
-    // second-level (shared-memory) counting needs the sub-list workspace; without it the L2-atomic kernel does the job
-    const int sub_bits = part->shift - 16;
-    // workspace of the second level (u16 units): segment lengths, [sub][cta][C3] segments, dump area of overflowing shares
-    L2Layout Y = {0, 0, 0, 0, 0};
-    // CTAs of k2_partition: two per SM, fewer when a bucket cannot have that many tiles anyway (small inputs keep big segments)
-    const unsigned grid2 = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * 2, 1024),
-                                                            part->capacity / ((uint64_t)kStepSlots * std::max(1, part->n_buckets))));
-    if (part->sub && sub_bits >= 0) {
-        Y.nsub = 1u << sub_bits;
-        Y.n_cta = grid2;
-        Y.seg0 = ((uint64_t)Y.nsub * Y.n_cta * 2 + 7) & ~7ull;
-        const uint64_t segs = (uint64_t)Y.nsub * Y.n_cta;
-        uint64_t C3 = part->sub_capacity > Y.seg0 + kStepSlots ? ((part->sub_capacity - Y.seg0 - kStepSlots) / segs) & ~7ull : 0;
-        if (segs * C3 + kStepSlots >= (1ull << 32)) C3 = ((((1ull << 32) - 8 - kStepSlots) / segs)) & ~7ull;
-        Y.C3 = (uint32_t)C3;
-        Y.dump = Y.seg0 + segs * C3;
+    // second-level (shared-memory) counting needs the sub-slice lists built by add(); without them the L2-atomic kernel does the job
+    const bool smem_count = do_count && (mode & 4) && part->l2_enabled;
+    L2Layout Y = {0, 0, 0, 0, 0, 0};
+    if (smem_count) {
+        Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets;
+        Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
     }
-    const uint64_t C2 = Y.C3;
-    const bool smem_count = do_count && (mode & 4) && C2 >= 8;
     if (do_search) {
         if (!hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: search needs hist and sums");
         if (!part->has_rids) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: partition was built without read ids");
@@ -871,17 +899,10 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const char* un_env = getenv("LRB_SEARCH_UNROLL");  // gathers in flight per lane: 4 (default) or 8
     const bool unroll8 = un_env && atoi(un_env) == 8;
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
-    constexpr int kSmemL2 = 3 * kStepSlots * (int)sizeof(uint32_t);
-    if (smem_count) {
-        LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
-        LRB_CUDA(cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2));
-    }
+    if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
     for (int b = 0; b < part->n_buckets; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
-        if (smem_count) {
-            k2_partition<<<grid2, kL2Threads, kSmemL2, st>>>(part->keys, const_cast<PartMeta*>(meta), b, part->n_chunks, sub_bits, part->sub, Y);
-            k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, table);
-        }
+        if (smem_count) k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, table);
         if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table, smem_count ? 1 : 0);
         if (do_search) {
 #define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \

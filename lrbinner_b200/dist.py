@@ -70,14 +70,14 @@ class CudaEngine:
             self._rb = self.dr.read_blk.cpu().numpy().view(np.uint32)
         return int(self._rb[lo]), int(self._rb[hi])
 
-    def _partition(self, read_lo, read_hi, key_lo, key_hi):
+    def _partition(self, read_lo, read_hi, key_lo, key_hi, count=True):
         rect = (read_lo, read_hi, key_lo, key_hi)
         if self._rect != rect:
             blo, bhi = self._blocks(read_lo, read_hi)
             shift = self.shift
             while (key_hi - key_lo) >> shift > 64:
                 shift += 1
-            self.ws.build(True, blo, bhi, key_lo, key_hi, shift, grow=rect not in self._verified)
+            self.ws.build(True, blo, bhi, key_lo, key_hi, shift, grow=rect not in self._verified, count=count)
             self._verified.add(rect)       # same reads, same rectangle -> same size: later steps stay asynchronous
             self._rect = rect
 
@@ -94,7 +94,7 @@ class CudaEngine:
         self.p.dev_mirror(table)
 
     def search(self, table, bin_size, bins, hist, sums, read_lo, read_hi, key_lo, key_hi):
-        self._partition(read_lo, read_hi, key_lo, key_hi)
+        self._partition(read_lo, read_hi, key_lo, key_hi, count=False)   # re-used from count() when the rectangle is the same
         self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums)
 
 

@@ -278,8 +278,9 @@ class PartitionWorkspace:
         self.dr = dr
         self.capacity = int(capacity if capacity is not None else max(dr.n_blocks * 32, 1))
         self.keys = torch.empty(self.capacity, dtype=torch.int32, device=dr.device)
-        # second-level lists of the shared-memory count (2 B per entry of ONE bucket at a time, with headroom)
-        self.sub_capacity = int(sub_capacity if sub_capacity is not None else max(self.capacity // 4, 1 << 16) + 8192)
+        # second-level lists of the shared-memory count: 2 B per window, fixed-size segments -> 2x headroom (3x for small sets)
+        self.sub_capacity = int(sub_capacity if sub_capacity is not None
+                                else (2 if self.capacity >= (1 << 28) else 3) * self.capacity + (1 << 22))
         self.sub = torch.empty(self.sub_capacity, dtype=torch.int16, device=dr.device) if self.sub_capacity else None
         self.small = torch.zeros(_lib.PART_SMALL_U64, dtype=torch.int64, device=dr.device)
         self.step_capacity = int(lib.lrb_partition_step_capacity(dr.n_blocks, max_chunks))
@@ -290,7 +291,9 @@ class PartitionWorkspace:
                                    sub=self.sub.data_ptr() if self.sub is not None else None, capacity=self.capacity,
                                    sub_capacity=self.sub_capacity, step_capacity=self.step_capacity)
 
-    def begin(self, with_rids=True, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24):
+    def begin(self, with_rids=True, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, count=True):
+        """count=False: the partition will only be searched — skip building the second-level (count) lists."""
+        self.part.sub = self.sub.data_ptr() if (count and self.sub is not None) else None
         check(lib.lrb_dev_partition_begin(C.byref(self.part), 1 if with_rids else 0, key_lo, min(key_hi, _lib.TABLE_ENTRIES),
                                           log2_bucket_keys, _stream()))
 
@@ -298,8 +301,9 @@ class PartitionWorkspace:
         check(lib.lrb_dev_partition_add(C.byref(self.dr.view), C.c_void_p(self.blk_read.data_ptr()), blk_lo,
                                         self.dr.n_blocks if blk_hi is None else blk_hi, C.byref(self.part), _stream()))
 
-    def build(self, with_rids=True, blk_lo=0, blk_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, grow=False):
-        self.begin(with_rids, key_lo, key_hi, log2_bucket_keys)
+    def build(self, with_rids=True, blk_lo=0, blk_hi=None, key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, grow=False,
+              count=True):
+        self.begin(with_rids, key_lo, key_hi, log2_bucket_keys, count)
         self.add(blk_lo, blk_hi)
         if grow:      # verify (synchronises); if the lists did not fit, the device told us the size: grow once and redo
             needed = C.c_uint64(0)
@@ -311,7 +315,13 @@ class PartitionWorkspace:
                 self.capacity = int(needed.value) + int(needed.value) // 64 + 1024
                 self.keys = torch.empty(self.capacity, dtype=torch.int32, device=self.dr.device)
                 self.part.keys, self.part.capacity = self.keys.data_ptr(), self.capacity
-                self.begin(with_rids, key_lo, key_hi, log2_bucket_keys)
+                if self.sub is not None and self.sub_capacity < 2 * self.capacity:
+                    self.sub = None
+                    torch.cuda.empty_cache()
+                    self.sub_capacity = 2 * self.capacity + (1 << 22)
+                    self.sub = torch.empty(self.sub_capacity, dtype=torch.int16, device=self.dr.device)
+                    self.part.sub_capacity = self.sub_capacity
+                self.begin(with_rids, key_lo, key_hi, log2_bucket_keys, count)
                 self.add(blk_lo, blk_hi)
                 rc = lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream())
             check(rc)
@@ -334,7 +344,7 @@ def dev_table15_partitioned(dr, ws, table, do_count=True, bin_size=1, bins=1, hi
                             key_lo=0, key_hi=_lib.TABLE_ENTRIES, log2_bucket_keys=24, smem_count=True):
     """One-shot: partition the windows of [blk_lo, blk_hi) x [key_lo, key_hi), then count and/or search per bucket."""
     search = hist is not None
-    ws.build(search, blk_lo, blk_hi, key_lo, key_hi, log2_bucket_keys)
+    ws.build(search, blk_lo, blk_hi, key_lo, key_hi, log2_bucket_keys, count=do_count and smem_count)
     ws.apply(table, do_count, search, bin_size, bins, hist, sums, smem_count=smem_count)
 
 

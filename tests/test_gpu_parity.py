@@ -367,9 +367,9 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
         table_p = z(2 ** 30)
         dev_table15_partitioned(dr, ws, table_p, True, **kw)
         assert torch.equal(table_p, table_d), kw
-    n_cta = max(1, min(2 * torch.cuda.get_device_properties(DEV).multi_processor_count, ws.capacity // (8192 * 64)))
-    # room for 8 entries per (sub-slice, CTA) segment: every tile overflows its shares, every bucket falls back
-    tiny = PartitionWorkspace(dr, sub_capacity=256 * n_cta * (2 + 8) + 8192 + 64)
+    # barely enough room for the second-level lists: many (bucket, sub-slice, CTA) segments overflow and their buckets fall
+    # back to the L2-atomic kernel, the others go through shared memory — one table
+    tiny = PartitionWorkspace(dr, sub_capacity=int(1.3 * ws.capacity) + (1 << 20))
     table_p = torch.full((2 ** 30,), 7, dtype=torch.int32, device=DEV)
     dev_table15_partitioned(dr, tiny, table_p, True)
     dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=25)

@@ -10,6 +10,6 @@ done
 
 for spec in k2_partition:6 k_count_smem:6; do
   kn=${spec%%:*}; skip=${spec##*:}
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $skip -c 1 -f -o gpurun_out/r01l_$kn python tools/prof_step.py --reads 1000000 --steps 1 > gpurun_out/ncu_$kn.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kn -s $skip -c 1 -f -o gpurun_out/r01m_$kn python tools/prof_step.py --reads 1000000 --steps 1 > gpurun_out/ncu_$kn.log 2>&1
   echo "ncu $kn rc=$?"
 done
