@@ -360,155 +360,185 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
 //
 // k2_partition runs once per chunk, right after k_partition (so in the host pipeline it sits in the shadow of the
 // host-to-device copy of the next chunk): persistent CTAs take tiles of 8192 entries of the chunk's bucket regions
-// round-robin.  The tile arrives in shared memory through cp.async while the previous one is processed (double
-// buffer); per tile: count per sub-slice (smem REDs), scan, rank + place into a staging array, linear sweep out (the
-// staged word carries its sub-slice).  Every CTA appends to its OWN segment of every (bucket, sub-slice) list
-// ([bucket][sub][cta][C3] entries; fill counters in a private global row), so there is no reservation between CTAs
-// and no ordering; list order is irrelevant for counting.  Segments have a fixed capacity (a multiple of the expected
-// fill); a bucket whose keys are skewed enough to overflow one raises overflow2[bucket] and is counted by
-// k_count_keys instead (both count kernels look at the flag); its stray entries go to the bucket's dump area.
-// Workspace (u16 units): fill[n_cta][n_buckets * nsub] as u32, then per bucket its segments + a dump area.
-constexpr int kL2Threads = 512;   // 16 entries per thread: twice the warps of a 256-thread shape at the same shared-memory footprint
+// round-robin.  Every entry is touched ONCE: it arrives in a register (the next tile's entries are fetched while the
+// current ones are swept), takes the next slot of its sub-slice's staging row with one returning shared-memory atomic
+// and drops its low 15 key bits there (2-byte staging, kL2Stage slots = 4x the expected share per sub-slice, so no
+// count pass and no scan are needed); after one barrier each warp sweeps the rows of the sub-slices it owns into the
+// lists (contiguous 2-byte stores).  The few entries that find their row full go through a small overflow list that
+// the owning warp appends after the row.  Every CTA appends to its OWN segment of every (bucket, sub-slice) list
+// ([bucket][sub][cta][C3] entries; fill counters in a private global row, read and written only by the owning lane),
+// so there is no reservation between CTAs and no ordering; list order is irrelevant for counting.  Segments have a
+// fixed capacity (a multiple of the expected fill); a bucket whose keys are skewed enough to overflow a segment (or
+// the per-tile overflow list) raises overflow2[bucket] and is counted by k_count_keys instead (both count kernels look
+// at the flag).  Workspace (u16 units): fill[n_cta][n_buckets * nsub] as u32, then per bucket its segments.
+constexpr int kL2Threads = 512;   // 16 entries per thread
+constexpr int kL2Warps = kL2Threads / 32;
 constexpr int kL2PerThread = kStepSlots / kL2Threads;
-
-__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// fire-and-forget shared-memory increment (plain RED: with hundreds of bins the lanes of a warp rarely collide, so
-// the warp-aggregated form the compiler emits for atomicAdd(p, 1) only adds instructions)
-__device__ __forceinline__ void smem_inc(uint32_t* p) {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-}
+constexpr int kL2Stage = 32768;   // u16 staging slots (64 KB): rows of kL2Stage / nsub slots
+constexpr int kL2Ovl = 1536;      // entries of a tile that may miss their staging row before the bucket falls back
+constexpr int kL2CtasPerSm = 2;   // measured: a third CTA per SM (fits: 40 registers, 74 KB) makes the kernel 40 % slower (l1tex is already 80 % busy)
 
 struct L2Layout {
     uint32_t nsub, n_cta, C3, nb;   // sub-slices per bucket, CTAs of k2_partition, entries per segment, buckets
-    uint64_t seg0, span;            // first segment; u16 units per bucket (its segments + the dump area)
+    uint32_t cta_major;             // segment order inside a bucket: [cta][sub] (1) or [sub][cta] (0)
+    uint32_t strided;               // k2_partition row ownership (fill rows are permuted to match)
+    __host__ __device__ uint32_t seg(uint32_t sub, uint32_t cta) const { return cta_major ? cta * nsub + sub : sub * n_cta + cta; }
+    // position of a sub-slice's counter in a fill row: the sub-slices warp + 16 j that one k2_partition warp owns sit next to
+    // each other, so its lanes read and write one 64-byte stretch instead of 16 sectors
+    __host__ __device__ uint32_t fill_pos(uint32_t sub) const { return (sub & 15u) * (nsub >> 4) + (sub >> 4); }
+    uint64_t seg0, span;            // first segment; u16 units per bucket (its segments + a spare tile)
     __host__ __device__ uint64_t bucket_base(uint32_t b) const { return seg0 + (uint64_t)b * span; }
-    __host__ __device__ uint32_t dump_delta() const { return nsub * n_cta * C3; }  // inside the bucket's span
 };
 
-__global__ void __launch_bounds__(kL2Threads, 2)
+template <int LOG2_NSUB, bool STRIDED>
+__global__ void __launch_bounds__(kL2Threads, kL2CtasPerSm)
 k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int c, uint16_t* __restrict__ ws, L2Layout Y) {
     extern __shared__ uint32_t s_dyn[];
-    uint32_t* s_tile = s_dyn;                      // [2][kStepSlots]  tile double buffer
-    uint32_t* s_stage = s_dyn + 2 * kStepSlots;    // [kStepSlots]     (sub << 15) | low 15 key bits, grouped by sub-slice
+    uint16_t* s_stage = reinterpret_cast<uint16_t*>(s_dyn);  // [nsub][cap] low 15 key bits
     __shared__ uint32_t s_cnt[kMaxSubs];           // entries of the tile per sub-slice (zero between tiles)
-    __shared__ uint32_t s_cur[kMaxSubs];           // staging cursor
-    __shared__ uint32_t s_delta[kMaxSubs];         // list position (inside the bucket's span) of staged position i = i + s_delta
-    __shared__ uint32_t s_wsum[kL2Threads / 32];
+    __shared__ uint32_t s_ovl[kL2Ovl];             // (sub << 15) | low key bits of the entries that found their row full
+    __shared__ uint32_t s_novl[2];                 // length of s_ovl, by tile parity
     __shared__ uint32_t s_tiles0[kMaxBuckets + 1]; // first tile of each bucket region of the chunk
+    __shared__ ull s_reg_n[kMaxBuckets], s_reg_off[kMaxBuckets];
     __shared__ uint32_t s_ovf[kMaxBuckets];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t nsub = Y.nsub, sub_mask = nsub - 1u;
+    constexpr uint32_t nsub = 1u << LOG2_NSUB, sub_mask = nsub - 1u;   // == Y.nsub
+    constexpr uint32_t cap = (uint32_t)kL2Stage / nsub, cap_shift = 15u - LOG2_NSUB;
+    constexpr uint32_t spw = nsub / kL2Warps;      // sub-slices owned by a warp: warp * spw + j, j < spw (nsub >= 16)
     if (meta->overflow) return;  // lists incomplete: nothing is applied anywhere
     uint32_t* __restrict__ fill = reinterpret_cast<uint32_t*>(ws) + (size_t)blockIdx.x * Y.nb * nsub;  // this CTA's row
     for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) s_cnt[i] = 0;
-    if (tid < (uint32_t)kMaxBuckets) s_ovf[tid] = 0;
+    if (tid < (uint32_t)kMaxBuckets) {
+        s_ovf[tid] = 0;
+        s_reg_n[tid] = tid < Y.nb ? meta->counts[c][tid] : 0ull;
+        s_reg_off[tid] = tid < Y.nb ? meta->offsets[c][tid] : 0ull;
+    }
+    if (tid < 2) s_novl[tid] = 0;
+    __syncthreads();
     if (tid == 0) {  // tiles of the chunk, numbered across its bucket regions
         uint32_t acc = 0;
         for (uint32_t b = 0; b < Y.nb; ++b) {
             s_tiles0[b] = acc;
-            acc += (uint32_t)((meta->counts[c][b] + kStepSlots - 1) / kStepSlots);
+            acc += (uint32_t)((s_reg_n[b] + kStepSlots - 1) / kStepSlots);
         }
         for (uint32_t b = Y.nb; b <= (uint32_t)kMaxBuckets; ++b) s_tiles0[b] = acc;
     }
     __syncthreads();
     const uint32_t total_tiles = s_tiles0[Y.nb];
-    auto locate = [&](uint32_t tile, uint32_t& b, const uint32_t*& src, uint32_t& n_tile) {
-        uint32_t lo = 0, hi = Y.nb;  // last bucket whose first tile is <= tile
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_tiles0[mid] <= tile) lo = mid; else hi = mid;
-        }
-        b = lo;
+    uint32_t b_loc = 0;  // tiles ascend: the bucket only moves forward
+    auto fetch = [&](uint32_t tile, uint32_t (&e)[kL2PerThread], uint32_t& b, uint32_t& n_tile) {
+        while (tile >= s_tiles0[b_loc + 1]) ++b_loc;
+        b = b_loc;
         const uint32_t t = tile - s_tiles0[b];
-        const uint64_t n_reg = meta->counts[c][b];
-        n_tile = (uint32_t)min((uint64_t)kStepSlots, n_reg - (uint64_t)t * kStepSlots);
-        src = ents + meta->offsets[c][b] + (uint64_t)t * kStepSlots;
-    };
-    auto issue = [&](uint32_t tile, int buf, uint32_t& b, uint32_t& n_tile) {
-        const uint32_t* src;
-        locate(tile, b, src, n_tile);
-        uint32_t* dst = s_tile + buf * kStepSlots;
+        n_tile = (uint32_t)min((ull)kStepSlots, s_reg_n[b] - (ull)t * kStepSlots);
+        const uint32_t* __restrict__ src = ents + s_reg_off[b] + (ull)t * kStepSlots;
+        if (n_tile == (uint32_t)kStepSlots) {
 #pragma unroll
-        for (int j = 0; j < kL2PerThread; ++j) {
-            const uint32_t i = j * (uint32_t)kL2Threads + tid;
-            if (i < n_tile) cp_async4(dst + i, src + i);
+            for (int j = 0; j < kL2PerThread; ++j) e[j] = __ldcs(src + j * kL2Threads + tid);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kL2PerThread; ++j) e[j] = (j * kL2Threads + tid < n_tile) ? __ldcs(src + j * kL2Threads + tid) : 0u;
         }
-        cp_async_commit();
     };
-    uint32_t tile = blockIdx.x;
-    uint32_t n_cur = 0, n_next = 0, b_cur = 0, b_next = 0;
-    if (tile < total_tiles) issue(tile, 0, b_cur, n_cur);
-    for (int it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
+    const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
+    const uint32_t my_sub = STRIDED ? warp + (uint32_t)kL2Warps * lane : warp * spw + lane;  // lane j < spw looks after the fill counter of this sub-slice (contiguous: no bank conflicts)
+    const uint32_t my_pos = STRIDED ? Y.fill_pos(my_sub) : my_sub;   // its counter in the fill row
+    uint32_t e[kL2PerThread];
+    uint32_t tile = blockIdx.x, n_cur = 0, n_next = 0, b_cur = 0, b_next = 0;
+    if (tile < total_tiles) fetch(tile, e, b_cur, n_cur);
+    for (uint32_t it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t par = it & 1u;
         const uint32_t nxt = tile + gridDim.x;
-        if (nxt < total_tiles) { issue(nxt, buf ^ 1, b_next, n_next); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         uint32_t* frow = fill + (size_t)b_cur * nsub;
-        const uint32_t f0 = tid < nsub ? frow[tid] : 0u;  // travels while the tile is counted
-        __syncthreads();  // the tile has landed for every thread; the previous sweep is over
-        const uint32_t* tile_e = s_tile + buf * kStepSlots;
-        const bool full = n_cur == kStepSlots;
-        if (full) {
+        const uint32_t f_my = lane < spw ? frow[my_pos] : 0u;    // written only by this lane (previous tiles of this CTA)
+        // place: one returning atomic + one predicated 2-byte store per entry (the staged half-word keeps entry bit 15, a
+        // sub-slice bit: k_count_smem masks it off); entries that find their row full are remembered in a bit mask and go
+        // to the overflow list afterwards
+        uint32_t spill = 0;
+        auto place = [&](int j) {
+            const uint32_t sub = (e[j] >> kSubBits) & sub_mask;
+            const uint32_t idx = atomicAdd(&s_cnt[sub], 1u);
+            // rows fill at the same pace: rotate each by its sub-slice so equal idx means different banks
+            if (idx < cap) s_stage[(sub << cap_shift) + ((idx + 2u * sub) & (cap - 1u))] = (uint16_t)e[j];
+            else spill |= 1u << j;
+        };
+        if (n_cur == (uint32_t)kStepSlots) {
 #pragma unroll
-            for (int j = 0; j < kL2PerThread; ++j) smem_inc(&s_cnt[(tile_e[j * kL2Threads + tid] >> kSubBits) & sub_mask]);
+            for (int j = 0; j < kL2PerThread; ++j) place(j);
         } else {
-            for (uint32_t i = tid; i < n_cur; i += kL2Threads) smem_inc(&s_cnt[(tile_e[i] >> kSubBits) & sub_mask]);
-        }
-        __syncthreads();
-        {   // exclusive scan over the sub-slices (one per thread); append position in this CTA's segments
-            const uint32_t c0 = s_cnt[tid];
-            s_cnt[tid] = 0;
-            uint32_t x = c0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-                if (lane >= (uint32_t)d) x += y;
-            }
-            if (lane == 31) s_wsum[warp] = x;
-            __syncthreads();
-            uint32_t base = 0;
-            for (uint32_t w = 0; w < warp; ++w) base += s_wsum[w];
-            const uint32_t ex0 = base + x - c0;
-            const bool o0 = f0 + c0 > Y.C3;
-            if (o0) s_ovf[b_cur] = 1u;
-            // segment of (sub, this CTA) starts at (sub * n_cta + cta) * C3 inside the bucket's span
-            s_delta[tid] = o0 ? Y.dump_delta() : (tid * Y.n_cta + blockIdx.x) * Y.C3 + f0 - ex0;
-            if (tid < nsub && c0 && !o0) frow[tid] = f0 + c0;
-            s_cur[tid] = ex0;
+            for (int j = 0; j < kL2PerThread; ++j)
+                if (j * kL2Threads + tid < n_cur) place(j);
         }
-        __syncthreads();
-        const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
-        if (full) {
+        if (spill) {
 #pragma unroll
             for (int j = 0; j < kL2PerThread; ++j) {
-                const uint32_t e = tile_e[j * kL2Threads + tid];
-                s_stage[atomicAdd(&s_cur[(e >> kSubBits) & sub_mask], 1u)] = e & stage_mask;
-            }
-        } else {
-            for (uint32_t i = tid; i < n_cur; i += kL2Threads) {
-                const uint32_t e = tile_e[i];
-                s_stage[atomicAdd(&s_cur[(e >> kSubBits) & sub_mask], 1u)] = e & stage_mask;
+                if ((spill >> j) & 1u) {
+                    const uint32_t o = atomicAdd(&s_novl[par], 1u);
+                    if (o < (uint32_t)kL2Ovl) s_ovl[o] = e[j] & stage_mask;
+                }
             }
         }
+        // the next tile's entries travel during the sweep, into the registers the placed ones just left (a fetch issued
+        // BEFORE the place phase would share its scoreboard with the loads the place phase waits for, and stall it)
+        if (nxt < total_tiles) fetch(nxt, e, b_next, n_next);
         __syncthreads();
+        // sweep: the rows of this warp's sub-slices go to this CTA's segments.  The owning lane works out where its row
+        // goes (a 32-bit position inside the bucket's span) and how much of it; the copy loop is then two predicated
+        // 2-byte copies per row (the expected row holds 8192 / nsub = cap / 4 entries)
+        const uint32_t novl_raw = s_novl[par];
+        const uint32_t n_my = lane < spw ? s_cnt[my_sub] : 0u;
+        const bool ok_my = f_my + n_my <= Y.C3;   // a full segment takes nothing more (its bucket falls back)
+        uint32_t ns_my = 0, off_my = 0;
+        if (lane < spw && n_my) {
+            s_cnt[my_sub] = 0;
+            if (ok_my) {
+                frow[my_pos] = f_my + n_my;
+                ns_my = min(n_my, cap);
+                off_my = Y.seg(my_sub, blockIdx.x) * Y.C3 + f_my;   // < 2^32 (lrb_dev_partition_begin clamps C3)
+            } else {
+                s_ovf[b_cur] = 1u;
+            }
+        }
+        if (tid == 0) {
+            s_novl[par ^ 1u] = 0;  // the next tile's list; last read before the previous tile's closing barrier
+            if (novl_raw > (uint32_t)kL2Ovl) s_ovf[b_cur] = 1u;  // entries were dropped: k_count_keys counts this bucket
+        }
         uint16_t* __restrict__ lists = ws + Y.bucket_base(b_cur);
-        if (full) {
+        constexpr uint32_t cm = cap - 1u;
+        const uint32_t big = __ballot_sync(0xFFFFFFFFu, ns_my > 64u || (ok_my && n_my > cap));  // rows the fast loop does not finish
 #pragma unroll
-            for (int j = 0; j < kL2PerThread; ++j) {
-                const uint32_t i = j * kL2Threads + tid;
-                const uint32_t r = s_stage[i];
-                lists[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
-            }
-        } else {
-            for (uint32_t i = tid; i < n_cur; i += kL2Threads) {
-                const uint32_t r = s_stage[i];
-                lists[s_delta[r >> kSubBits] + i] = (uint16_t)(r & ((1u << kSubBits) - 1u));
+        for (uint32_t jj = 0; jj < spw; ++jj) {
+            const uint32_t ns = __shfl_sync(0xFFFFFFFFu, ns_my, jj);
+            const uint32_t off = __shfl_sync(0xFFFFFFFFu, off_my, jj) + lane;
+            const uint32_t sub = (STRIDED ? warp + (uint32_t)kL2Warps * jj : warp * spw + jj);
+            const uint16_t* src = s_stage + (sub << cap_shift);
+            const uint32_t p0 = (lane + 2u * sub) & cm, p1 = (lane + 32u + 2u * sub) & cm;
+            if (lane < ns) lists[off] = src[p0];
+            if (lane + 32u < ns) lists[off + 32u] = src[p1];
+        }
+        for (uint32_t rest = big; rest; rest &= rest - 1u) {  // rare: long rows, rows that spilled into the overflow list
+            const uint32_t jj = (uint32_t)__ffs(rest) - 1u;
+            const uint32_t ns = __shfl_sync(0xFFFFFFFFu, ns_my, jj), n = __shfl_sync(0xFFFFFFFFu, n_my, jj);
+            const uint32_t sub = (STRIDED ? warp + (uint32_t)kL2Warps * jj : warp * spw + jj);
+            uint16_t* __restrict__ dst = lists + __shfl_sync(0xFFFFFFFFu, off_my, jj);
+            const uint16_t* src = s_stage + (sub << cap_shift);
+            for (uint32_t j = lane + 64u; j < ns; j += 32) dst[j] = src[(j + 2u * sub) & cm];
+            if (n > cap) {
+                const uint32_t novl = min(novl_raw, (uint32_t)kL2Ovl);
+                uint32_t base = ns;
+                for (uint32_t i0 = 0; i0 < novl; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const uint32_t r = i < novl ? s_ovl[i] : 0xFFFFFFFFu;
+                    const bool mine = i < novl && (r >> kSubBits) == sub;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
+                    const uint32_t at = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    if (mine && at < n) dst[at] = (uint16_t)(r & 0x7FFFu);
+                    base += (uint32_t)__popc(bal);
+                }
             }
         }
+        __syncthreads();
         n_cur = n_next;
         b_cur = b_next;
     }
@@ -523,17 +553,17 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     extern __shared__ uint32_t s_tab[];  // 2^15
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, sub = blockIdx.x;
     if (meta->overflow || meta->overflow2[bucket]) return;
-    const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + sub;  // + cta * nb * nsub
+    const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + (Y.strided ? Y.fill_pos(sub) : sub);  // + cta * nb * nsub
     const size_t fill_stride = (size_t)Y.nb * Y.nsub;
     const uint16_t* __restrict__ lists = ws + Y.bucket_base(bucket);
     uint4* tab4 = reinterpret_cast<uint4*>(s_tab);
     for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) tab4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    auto bump8 = [&](const uint4& v) {
-        atomicAdd(&s_tab[v.x & 0xFFFFu], 1u); atomicAdd(&s_tab[v.x >> 16], 1u);
-        atomicAdd(&s_tab[v.y & 0xFFFFu], 1u); atomicAdd(&s_tab[v.y >> 16], 1u);
-        atomicAdd(&s_tab[v.z & 0xFFFFu], 1u); atomicAdd(&s_tab[v.z >> 16], 1u);
-        atomicAdd(&s_tab[v.w & 0xFFFFu], 1u); atomicAdd(&s_tab[v.w >> 16], 1u);
+    auto bump8 = [&](const uint4& v) {  // list entries are 16 bits wide; bit 15 is not part of the key inside the sub-slice
+        atomicAdd(&s_tab[v.x & 0x7FFFu], 1u); atomicAdd(&s_tab[(v.x >> 16) & 0x7FFFu], 1u);
+        atomicAdd(&s_tab[v.y & 0x7FFFu], 1u); atomicAdd(&s_tab[(v.y >> 16) & 0x7FFFu], 1u);
+        atomicAdd(&s_tab[v.z & 0x7FFFu], 1u); atomicAdd(&s_tab[(v.z >> 16) & 0x7FFFu], 1u);
+        atomicAdd(&s_tab[v.w & 0x7FFFu], 1u); atomicAdd(&s_tab[(v.w >> 16) & 0x7FFFu], 1u);
     };
     // a warp per segment (a few KB each), 16 B vectors.  The lengths of the warp's segments are fetched in one go and
     // the first four vectors of the next segment travel while the current one is counted.
@@ -541,7 +571,7 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     const uint32_t my_len = my_cta < Y.n_cta ? __ldg(fill + my_cta * fill_stride) : 0u;
     const uint32_t n_seg = (Y.n_cta > warp) ? (Y.n_cta - warp + 31u) / 32u : 0u;   // segments of this warp (n_cta <= 1024)
     bool any = __any_sync(0xFFFFFFFFu, my_len != 0u);
-    auto seg_ptr = [&](uint32_t k) { return lists + ((size_t)sub * Y.n_cta + (warp + 32u * k)) * Y.C3; };
+    auto seg_ptr = [&](uint32_t k) { return lists + (size_t)Y.seg(sub, warp + 32u * k) * Y.C3; };
     auto fetch4 = [&](uint32_t k, uint32_t n, uint4* v) {
         const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(seg_ptr(k));
         const uint32_t n8 = n / 8;
@@ -562,7 +592,7 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
             if (lane + 32u * u < n8) bump8(cur[u]);
         const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(src);
         for (uint32_t i = lane + 128u; i < n8; i += 32) bump8(__ldcs(src4 + i));      // long segments: the rest
-        for (uint32_t i = n8 * 8 + lane; i < n; i += 32) atomicAdd(&s_tab[src[i]], 1u);
+        for (uint32_t i = n8 * 8 + lane; i < n; i += 32) atomicAdd(&s_tab[src[i] & 0x7FFFu], 1u);
 #pragma unroll
         for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
         n = n_next;
@@ -700,6 +730,16 @@ __global__ void __launch_bounds__(256) k_row_sums(const uint32_t* __restrict__ h
     sums[r] = s;
 }
 
+uint32_t l2_cta_major() {  // experiment switch (LRB_K2_LAYOUT=cta): segments of one k2_partition CTA next to each other
+    const char* e = getenv("LRB_K2_LAYOUT");
+    return (e && e[0] == 'c') ? 1u : 0u;
+}
+
+uint32_t l2_strided() {  // which rows a k2_partition warp sweeps: "strided" (warp + 16 j, default: 2 ms faster) or "block" (16 warp + j)
+    const char* e = getenv("LRB_K2_ROWS");
+    return (e && e[0] == 'b') ? 0u : 1u;
+}
+
 int sms() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -755,8 +795,8 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
     const int sub_bits = shift - 16;
     if (part->sub && sub_bits >= 0) {
         const uint64_t nsub = 1ull << sub_bits;
-        // CTAs of k2_partition: two per SM, fewer when the lists cannot have that many tiles anyway (small inputs keep big segments)
-        const uint64_t n_cta = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * 2, 1024), part->capacity / ((uint64_t)kStepSlots * nb)));
+        // CTAs of k2_partition: kL2CtasPerSm per SM, fewer when the lists cannot have that many tiles anyway (small inputs keep big segments)
+        const uint64_t n_cta = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * kL2CtasPerSm, 1024), part->capacity / ((uint64_t)kStepSlots * nb)));
         const uint64_t seg0 = (n_cta * nb * nsub * 2 + 7) & ~7ull;               // fill counters (u32) in u16 units
         const uint64_t segs = (uint64_t)nb * nsub * n_cta;
         uint64_t C3 = part->sub_capacity > seg0 + (uint64_t)nb * kStepSlots ? ((part->sub_capacity - seg0 - (uint64_t)nb * kStepSlots) / segs) & ~7ull : 0;
@@ -810,11 +850,25 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
 #undef LRB_LAUNCH_PART
     if (part->l2_enabled) {
         L2Layout Y;
-        Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb;
+        Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
         Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
-        constexpr int kSmemL2 = 3 * kStepSlots * (int)sizeof(uint32_t);
-        LRB_CUDA(cudaFuncSetAttribute(k2_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2));
-        k2_partition<<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y);
+        constexpr int kSmemL2 = kL2Stage * (int)sizeof(uint16_t);
+#define LRB_LAUNCH_K2(LG)                                                                                               \
+    case LG:                                                                                                            \
+        if (strided) {                                                                                                  \
+            LRB_CUDA(cudaFuncSetAttribute(k2_partition<LG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2)); \
+            k2_partition<LG, true><<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y);            \
+        } else {                                                                                                        \
+            LRB_CUDA(cudaFuncSetAttribute(k2_partition<LG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2)); \
+            k2_partition<LG, false><<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y);           \
+        }                                                                                                               \
+        break
+        const bool strided = Y.strided != 0;
+        switch (shift - 16) {  // log2 of the sub-slices per bucket (shift is 20..25)
+            LRB_LAUNCH_K2(4); LRB_LAUNCH_K2(5); LRB_LAUNCH_K2(6); LRB_LAUNCH_K2(7); LRB_LAUNCH_K2(8); LRB_LAUNCH_K2(9);
+            default: return lrb_set_error(LRB_EINVAL, "second-level lists need log2_bucket_keys in [20, 25]");
+        }
+#undef LRB_LAUNCH_K2
     }
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
@@ -863,9 +917,9 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const bool do_count = mode & 1, do_search = mode & 2;
     // second-level (shared-memory) counting needs the sub-slice lists built by add(); without them the L2-atomic kernel does the job
     const bool smem_count = do_count && (mode & 4) && part->l2_enabled;
-    L2Layout Y = {0, 0, 0, 0, 0, 0};
+    L2Layout Y = {0, 0, 0, 0, 0, 0, 0, 0};
     if (smem_count) {
-        Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets;
+        Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
         Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
     }
     if (do_search) {
@@ -896,8 +950,8 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     // the gathers for the memory pipe), kept behind LRB_SEARCH_LUT=1 for experiments
     const char* lut_env = getenv("LRB_SEARCH_LUT");
     const bool use_lut = lut_env && atoi(lut_env) > 0 && ((uint64_t)bins + 1) * S32 < kBinLut;
-    const char* un_env = getenv("LRB_SEARCH_UNROLL");  // gathers in flight per lane: 4 (default) or 8
-    const bool unroll8 = un_env && atoi(un_env) == 8;
+    const char* un_env = getenv("LRB_SEARCH_UNROLL");  // gathers in flight per lane: 8 (default, 22.3 ms at config #2) or 4 (23.7 ms)
+    const bool unroll8 = !(un_env && atoi(un_env) == 4);
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
     if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
     for (int b = 0; b < part->n_buckets; ++b) {

@@ -12,7 +12,8 @@ against the finished table.  Three decompositions are imp
   plan "keyshard_ag" (B)  COUNT as in A, then all-gather of the table slices (4 GiB in total), local
         mirror, read-sharded SEARCH with no further communication.
   plan "readshard_ar" (X) every rank counts only ITS reads into a private full table; all-reduce(sum) of the
-        4 GiB tables; local mirror; read-sharded SEARCH.  No rank needs another rank's reads.
+        canonical half of the tables (2 GiB: count touches only the bit-15-clear member of {x, rc x}); local mirror;
+        read-sharded SEARCH.  No rank needs another rank's reads.
 
 u32 sums are associative mod 2^32, so every plan is bit-exact whatever the reduction order.
 Composition is read-sharded in all plans.  Each rank returns the rows of its own reads
@@ -56,6 +57,7 @@ class CudaEngine:
         self.n_reads = device_reads.n_reads
         self.device = device_reads.device
         self.table_entries = TABLE_ENTRIES          # 4^15 (count-15mers.cpp:99)
+        self.canon_bit = 15                         # count() touches only keys with this bit clear; mirror() fills the rest
         self.shift = log2_bucket_keys
         self._rb = None
         self.ws = profile.PartitionWorkspace(device_reads, capacity=workspace_entries)
@@ -108,6 +110,16 @@ def _reduce_scatter(dist, out, inp, group):
         dist.reduce_scatter_tensor(out, inp, group=group)
 
 
+def _all_reduce_canonical_half(dist, table, bit, group):
+    """Sum over ranks of the entries count() can have touched: keys whose middle-base high bit is clear, i.e. the lower
+    2^bit entries of every 2^(bit+1)-entry stretch — half the table, so half the bytes on NVLink.  The other half is
+    still zero everywhere (mirror() runs after the exchange)."""
+    canon = table.view(-1, 2, 1 << bit)[:, 0, :]
+    buf = canon.contiguous()
+    dist.all_reduce(buf, group=group)
+    canon.copy_(buf)
+
+
 def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None, comp_width=None, timers=None):
     """Runs the whole stage across the ranks of `group`.  Returns dict(comp, hist, sums, own=(lo, hi), table):
     comp/hist/sums hold the rows of this rank's own reads (row i <-> read own_lo + i)."""
@@ -137,7 +149,11 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
         if hi > lo:
             engine.count(table, 0, entries, lo, hi)
         mark("count")
-        dist.all_reduce(table, group=group)                      # 4 GiB u32 sum over NVLink
+        bit = getattr(engine, "canon_bit", None)
+        if bit is not None:
+            _all_reduce_canonical_half(dist, table, bit, group)  # 2 GiB u32 sum over NVLink
+        else:
+            dist.all_reduce(table, group=group)                  # whole table
         mark("exchange_table")
     else:
         engine.count(table, klo, khi, 0, n)                       # all reads, own keys: no communication

@@ -30,6 +30,7 @@ class OracleEngine:
         self.seqs = seqs
         self.n_reads = len(seqs)
         self.table_entries = 4 ** KT
+        self.canon_bit = KT          # middle base of a 9-mer = base 4 -> its high bit is bit 9
         self._sparse = {}
 
     def zeros(self, shape):

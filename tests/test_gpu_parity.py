@@ -396,6 +396,42 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
 
 
+def test_second_level_count_survives_key_skew():
+    """Low-complexity reads (tandem repeats, homopolymers) pile thousands of windows of one 8192-entry tile into a single
+    2^15-key sub-slice: k2_partition's fixed staging rows overflow into its per-tile overflow list, and where that (or a
+    list segment) overflows too the bucket falls back to k_count_keys.  Whatever the mix of paths, one table."""
+    rng = np.random.default_rng(77)
+    spec = SynthSpec(2500, seed=31, scale=0.05)
+    seqs = spec.host_sequences()
+    for _ in range(30):                                    # tandem repeats of a random unit of 6..9 bases, 2-6 kb
+        unit = bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(6, 10))).tolist())
+        seqs.append((unit * 1200)[:int(rng.integers(2000, 6000))])
+    seqs += [b"A" * 6000] * 40 + [b"T" * 5000] * 10        # homopolymers: one key, far beyond any staging row or overflow list
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    pr = PackedReads.from_sequences(seqs)
+    dr = DeviceReads(pr, DEV)
+    z = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=DEV)
+    table_d = z(2 ** 30)
+    dev_count(dr, table_d)
+    # roomy list segments, so that a repeat read's ~1000 windows of one key overflow only the per-tile staging row
+    ws = PartitionWorkspace(dr, sub_capacity=40 * pr.n_blocks * 32)
+    fell_back = {}
+    for shift in (24, 25, 22):
+        table_p = z(2 ** 30)
+        if shift == 22:                                    # 64 buckets of 2^22 keys cover a quarter of the key space at a time
+            for q in range(4):
+                dev_table15_partitioned(dr, ws, table_p, True, key_lo=q * 2 ** 28, key_hi=(q + 1) * 2 ** 28, log2_bucket_keys=22)
+        else:
+            dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=shift)
+            # PartMeta.overflow2 (csrc/partition.cu): counts, offsets [64][64] u64, chunk_base[65], needed, overflow, then u32[64]
+            o2 = ws.small[2 * 64 * 64 + 65 + 2:2 * 64 * 64 + 65 + 2 + 32].cpu().numpy().view(np.uint32)
+            fell_back[shift] = int(o2[:ws.part.n_buckets].astype(bool).sum())
+        assert torch.equal(table_p, table_d), shift
+    # the homopolymer bucket must have fallen back; most buckets must not have (they took the overflow-list path at worst)
+    assert 1 <= fell_back[24] <= 32, fell_back
+
+
 # ---- full-size properties (BASELINE.json configs) ---------------------------------------------------------
 
 def _full_size_properties(name, subsample=200):
