@@ -359,8 +359,8 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
 // partitioned once more by the next key bits into sub-slices of 2^15 keys whose counters fit one SM's shared memory.
 //
 // k2_partition runs once per chunk, right after k_partition (so in the host pipeline it sits in the shadow of the
-// host-to-device copy of the next chunk): persistent CTAs take tiles of 8192 entries of the chunk's bucket regions
-// round-robin.  Every entry is touched ONCE: it arrives in a register (the next tile's entries are fetched while the
+// host-to-device copy of the next chunk): persistent CTAs take tiles of 8192 entries of the chunk's bucket regions,
+// kL2Run consecutive tiles of one bucket at a time (schedule in the kernel).  Every entry is touched ONCE: it arrives in a register (the next tile's entries are fetched while the
 // current ones are swept), takes the next slot of its sub-slice's staging row with one returning shared-memory atomic
 // and drops its low 15 key bits there (2-byte staging, kL2Stage slots = 4x the expected share per sub-slice, so no
 // count pass and no scan are needed); after one barrier each warp sweeps the rows of the sub-slices it owns into the
@@ -376,6 +376,7 @@ constexpr int kL2Warps = kL2Threads / 32;
 constexpr int kL2PerThread = kStepSlots / kL2Threads;
 constexpr int kL2Stage = 32768;   // u16 staging slots (64 KB): rows of kL2Stage / nsub slots
 constexpr int kL2Ovl = 1536;      // entries of a tile that may miss their staging row before the bucket falls back
+constexpr uint32_t kL2Run = 8;    // consecutive tiles of one bucket a CTA takes at a time
 constexpr int kL2CtasPerSm = 2;   // measured: a third CTA per SM (fits: 40 registers, 74 KB) makes the kernel 40 % slower (l1tex is already 80 % busy)
 
 struct L2Layout {
@@ -398,7 +399,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     __shared__ uint32_t s_cnt[kMaxSubs];           // entries of the tile per sub-slice (zero between tiles)
     __shared__ uint32_t s_ovl[kL2Ovl];             // (sub << 15) | low key bits of the entries that found their row full
     __shared__ uint32_t s_novl[2];                 // length of s_ovl, by tile parity
-    __shared__ uint32_t s_tiles0[kMaxBuckets + 1]; // first tile of each bucket region of the chunk
+    __shared__ uint32_t s_tiles[kMaxBuckets], s_runs[kMaxBuckets], s_start[kMaxBuckets], s_runs0[kMaxBuckets];  // tile schedule (below)
     __shared__ ull s_reg_n[kMaxBuckets], s_reg_off[kMaxBuckets];
     __shared__ uint32_t s_ovf[kMaxBuckets];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -408,28 +409,63 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     if (meta->overflow) return;  // lists incomplete: nothing is applied anywhere
     uint32_t* __restrict__ fill = reinterpret_cast<uint32_t*>(ws) + (size_t)blockIdx.x * Y.nb * nsub;  // this CTA's row
     for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) s_cnt[i] = 0;
+    const uint32_t n_cta = gridDim.x;
     if (tid < (uint32_t)kMaxBuckets) {
         s_ovf[tid] = 0;
-        s_reg_n[tid] = tid < Y.nb ? meta->counts[c][tid] : 0ull;
+        const ull n_reg = tid < Y.nb ? meta->counts[c][tid] : 0ull;
+        s_reg_n[tid] = n_reg;
         s_reg_off[tid] = tid < Y.nb ? meta->offsets[c][tid] : 0ull;
+        const uint32_t tiles = (uint32_t)((n_reg + kStepSlots - 1) / kStepSlots);
+        s_tiles[tid] = tiles;
+        s_runs[tid] = (tiles + kL2Run - 1u) / kL2Run;
+        // runs of this bucket in the earlier chunks, and in chunk 0 (the base spread of the buckets over the CTAs)
+        uint32_t before = 0, runs0 = 0;
+        if (tid < Y.nb) {
+            for (int cc = 0; cc < c; ++cc) {
+                const uint32_t rr = (uint32_t)(((meta->counts[cc][tid] + kStepSlots - 1) / kStepSlots + kL2Run - 1u) / kL2Run);
+                before += rr;
+                if (cc == 0) runs0 = rr;
+            }
+            if (c == 0) runs0 = s_runs[tid];
+        }
+        s_start[tid] = before;
+        s_runs0[tid] = runs0;
     }
     if (tid < 2) s_novl[tid] = 0;
     __syncthreads();
-    if (tid == 0) {  // tiles of the chunk, numbered across its bucket regions
+    if (tid == 0) {
         uint32_t acc = 0;
         for (uint32_t b = 0; b < Y.nb; ++b) {
-            s_tiles0[b] = acc;
-            acc += (uint32_t)((s_reg_n[b] + kStepSlots - 1) / kStepSlots);
+            s_start[b] = (s_start[b] + acc) % n_cta;
+            acc += s_runs0[b];
         }
-        for (uint32_t b = Y.nb; b <= (uint32_t)kMaxBuckets; ++b) s_tiles0[b] = acc;
     }
     __syncthreads();
-    const uint32_t total_tiles = s_tiles0[Y.nb];
-    uint32_t b_loc = 0;  // tiles ascend: the bucket only moves forward
-    auto fetch = [&](uint32_t tile, uint32_t (&e)[kL2PerThread], uint32_t& b, uint32_t& n_tile) {
-        while (tile >= s_tiles0[b_loc + 1]) ++b_loc;
-        b = b_loc;
-        const uint32_t t = tile - s_tiles0[b];
+    // Tile schedule.  A RUN is kL2Run consecutive tiles of one bucket region; run r of bucket b belongs to CTA
+    // (start[b] + r) mod n_cta, where start[b] continues from chunk to chunk (runs of b in the earlier chunks) on top of
+    // chunk 0's global run numbering.  So (1) a CTA appends kL2Run tiles' worth to a segment while its frontier sectors
+    // are hot in L2 (with one tile per visit, as a chunked build would give, every append re-fetches a partial sector),
+    // (2) every (bucket, CTA) pair receives the same share of the bucket whatever the chunking (the segments have a fixed
+    // capacity), (3) the 64 windows of a launch tile the ring of CTAs evenly.
+    uint32_t gb = 0, gr = 0, gt = 0;  // generator state: bucket, run (of this CTA) in it, tile in the run
+    auto seek = [&]() {               // first run of this CTA in bucket gb or a later one
+        for (; gb < Y.nb; ++gb) {
+            gr = (blockIdx.x + n_cta - s_start[gb]) % n_cta;
+            if (gr < s_runs[gb]) { gt = 0; return true; }
+        }
+        return false;
+    };
+    auto advance = [&]() {
+        if (++gt < kL2Run && gr * kL2Run + gt < s_tiles[gb]) return true;
+        gt = 0;
+        gr += n_cta;
+        if (gr < s_runs[gb]) return true;
+        ++gb;
+        return seek();
+    };
+    auto fetch = [&](uint32_t (&e)[kL2PerThread], uint32_t& b, uint32_t& n_tile) {  // the generator's current tile
+        b = gb;
+        const uint32_t t = gr * kL2Run + gt;
         n_tile = (uint32_t)min((ull)kStepSlots, s_reg_n[b] - (ull)t * kStepSlots);
         const uint32_t* __restrict__ src = ents + s_reg_off[b] + (ull)t * kStepSlots;
         if (n_tile == (uint32_t)kStepSlots) {
@@ -444,11 +480,11 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     const uint32_t my_sub = STRIDED ? warp + (uint32_t)kL2Warps * lane : warp * spw + lane;  // lane j < spw looks after the fill counter of this sub-slice (contiguous: no bank conflicts)
     const uint32_t my_pos = STRIDED ? Y.fill_pos(my_sub) : my_sub;   // its counter in the fill row
     uint32_t e[kL2PerThread];
-    uint32_t tile = blockIdx.x, n_cur = 0, n_next = 0, b_cur = 0, b_next = 0;
-    if (tile < total_tiles) fetch(tile, e, b_cur, n_cur);
-    for (uint32_t it = 0; tile < total_tiles; tile += gridDim.x, ++it) {
+    uint32_t n_cur = 0, n_next = 0, b_cur = 0, b_next = 0;
+    bool have = seek();
+    if (have) fetch(e, b_cur, n_cur);
+    for (uint32_t it = 0; have; ++it) {
         const uint32_t par = it & 1u;
-        const uint32_t nxt = tile + gridDim.x;
         uint32_t* frow = fill + (size_t)b_cur * nsub;
         const uint32_t f_my = lane < spw ? frow[my_pos] : 0u;    // written only by this lane (previous tiles of this CTA)
         // place: one returning atomic + one predicated 2-byte store per entry (the staged half-word keeps entry bit 15, a
@@ -481,7 +517,8 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         }
         // the next tile's entries travel during the sweep, into the registers the placed ones just left (a fetch issued
         // BEFORE the place phase would share its scoreboard with the loads the place phase waits for, and stall it)
-        if (nxt < total_tiles) fetch(nxt, e, b_next, n_next);
+        have = advance();
+        if (have) fetch(e, b_next, n_next);
         __syncthreads();
         // sweep: the rows of this warp's sub-slices go to this CTA's segments.  The owning lane works out where its row
         // goes (a 32-bit position inside the bucket's span) and how much of it; the copy loop is then two predicated
