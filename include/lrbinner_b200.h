@@ -178,6 +178,11 @@ int lrb_dev_partition_build(const lrb_reads_view* dev, const uint32_t* blk_read,
 int lrb_dev_partition_check(const lrb_partition* part, uint64_t* needed, void* stream);
 int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint32_t* table, long bin_size, int bins, uint32_t* hist,
                             uint32_t* sums, void* stream);
+/* The same for the buckets [bucket_lo, bucket_hi) only (clamped): a multi-GPU driver exchanges the table slice of
+ * bucket b+1 (keys [key_lo + (b+1) << log2_bucket_keys, ...)) while bucket b is searched.  sums are rewritten by the call
+ * that includes the last bucket. */
+int lrb_dev_partition_apply_range(const lrb_partition* part, int mode, int bucket_lo, int bucket_hi, uint32_t* table,
+                                  long bin_size, int bins, uint32_t* hist, uint32_t* sums, void* stream);
 
 /* Pack ASCII on the device: bases[] (device, concatenated) -> codes/valid of `dev` (layout prebuilt). */
 int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, const uint64_t* offsets, void* stream);

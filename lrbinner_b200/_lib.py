@@ -79,6 +79,7 @@ _SIG = {
     "lrb_dev_partition_check": (C.c_int, [_P, _P, _P]),
     "lrb_dev_partition_build": (C.c_int, [C.POINTER(ReadsView), _P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _P, _P]),
     "lrb_dev_partition_apply": (C.c_int, [_P, C.c_int, _P, C.c_long, C.c_int, _P, _P, _P]),
+    "lrb_dev_partition_apply_range": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_long, C.c_int, _P, _P, _P]),
     "lrb_dev_pack_ascii": (C.c_int, [C.POINTER(ReadsView), _P, _P, _P]),
     "lrb_dev_format_composition": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),
     "lrb_dev_format_coverage": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P]),

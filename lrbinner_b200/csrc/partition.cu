@@ -950,7 +950,16 @@ extern "C" int lrb_dev_partition_check(const lrb_partition* part, uint64_t* need
 // mode bit 0: count (table[key] += 1), bit 1: search (hist/sums through table[key]); both = per bucket count then search
 extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint32_t* table, long bin_size, int bins,
                                        uint32_t* hist, uint32_t* sums, void* stream) {
+    return lrb_dev_partition_apply_range(part, mode, 0, LRB_PART_MAX_BUCKETS, table, bin_size, bins, hist, sums, stream);
+}
+
+// The same for the buckets [bucket_lo, bucket_hi) only (clamped to the partition's buckets): lets a multi-GPU driver
+// exchange the table slice of bucket b+1 while bucket b is searched.  sums are rewritten when the last bucket is included.
+extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode, int bucket_lo, int bucket_hi, uint32_t* table,
+                                             long bin_size, int bins, uint32_t* hist, uint32_t* sums, void* stream) {
     if (!part || !table) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: null argument");
+    if (bucket_lo < 0) bucket_lo = 0;
+    if (bucket_hi > part->n_buckets) bucket_hi = part->n_buckets;
     const bool do_count = mode & 1, do_search = mode & 2;
     // second-level (shared-memory) counting needs the sub-slice lists built by add(); without them the L2-atomic kernel does the job
     const bool smem_count = do_count && (mode & 4) && part->l2_enabled;
@@ -991,7 +1000,7 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
     const bool unroll8 = !(un_env && atoi(un_env) == 4);
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
     if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
-    for (int b = 0; b < part->n_buckets; ++b) {
+    for (int b = bucket_lo; b < bucket_hi; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
         if (smem_count) k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, table);
         if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table, smem_count ? 1 : 0);
@@ -1005,7 +1014,7 @@ extern "C" int lrb_dev_partition_apply(const lrb_partition* part, int mode, uint
 #undef LRB_LAUNCH_SEARCH
         }
     }
-    if (do_search && part->n_reads)
+    if (do_search && part->n_reads && bucket_hi == part->n_buckets)
         k_row_sums<<<(unsigned)((part->n_reads + 255) / 256), 256, 0, st>>>(hist, sums, part->n_reads, (uint32_t)bins);
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;

@@ -15,6 +15,10 @@ against the finished table.  Three decompositions are imp
         canonical half of the tables (2 GiB: count touches only the bit-15-clear member of {x, rc x}); local mirror;
         read-sharded SEARCH.  No rank needs another rank's reads.
 
+        The exchange is PIPELINED with the search: the table is summed slice by slice (one slice = one bucket of the
+        key partition, 32 MiB of canonical entries) on a side stream, and the main stream searches slice i as soon as
+        it has arrived while slices i+1.. are still on NVLink — the search of a slice reads only that slice.
+
 u32 sums are associative mod 2^32, so every plan is bit-exact whatever the reduction order.
 Composition is read-sharded in all plans.  Each rank returns the rows of its own reads
 [own_lo, own_hi) = equal contiguous chunks of ceil(N/G) reads.
@@ -92,12 +96,45 @@ class CudaEngine:
         self._partition(read_lo, read_hi, key_lo, key_hi)
         self.ws.apply(table, count=True)
 
+    def count_fed(self, table, read_lo, read_hi, chunks, per_chunk):
+        """count() over the whole key space with the reads arriving in chunks (the e2e pipeline: the partition of chunk j
+        runs while chunk j+1 is still on PCIe).  chunks = [(read_lo_j, read_hi_j), ...] covering [read_lo, read_hi);
+        per_chunk(j) is called before chunk j is touched (it makes the stream wait for the chunk and may run other
+        per-chunk work, e.g. the composition)."""
+        rect = (read_lo, read_hi, 0, self.table_entries)
+        self.ws.begin(True, 0, self.table_entries, self.shift, count=True)
+        for j, (rlo, rhi) in enumerate(chunks):
+            per_chunk(j)
+            blo, bhi = self._blocks(rlo, rhi)
+            self.ws.add(blo, bhi)
+        if rect not in self._verified:               # first time for this rectangle: verify the workspace (synchronises)
+            try:
+                self.ws.check()
+            except self.p._lib.LrbError:             # too small: every chunk has arrived by now, redo in one piece and grow
+                blo, bhi = self._blocks(read_lo, read_hi)
+                self.ws.build(True, blo, bhi, 0, self.table_entries, self.shift, grow=True, count=True)
+            self._verified.add(rect)
+        self._rect = rect
+        self.ws.apply(table, count=True)
+
     def mirror(self, table):
         self.p.dev_mirror(table)
 
     def search(self, table, bin_size, bins, hist, sums, read_lo, read_hi, key_lo, key_hi):
         self._partition(read_lo, read_hi, key_lo, key_hi, count=False)   # re-used from count() when the rectangle is the same
         self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums)
+
+    # -- slice-wise search (plan X pipelines the table exchange with it): slice i = bucket i of the partition count() built
+    def n_slices(self, read_lo, read_hi):
+        self._partition(read_lo, read_hi, 0, self.table_entries, count=False)
+        return self.ws.part.n_buckets
+
+    def slice_keys(self, i):
+        return i << self.ws.part.shift, (i + 1) << self.ws.part.shift
+
+    def search_slice(self, table, bin_size, bins, hist, sums, read_lo, read_hi, i):
+        self._partition(read_lo, read_hi, 0, self.table_entries, count=False)
+        self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums, bucket_lo=i, bucket_hi=i + 1)
 
 
 def _reduce_scatter(dist, out, inp, group):
@@ -120,7 +157,87 @@ def _all_reduce_canonical_half(dist, table, bit, group):
     canon.copy_(buf)
 
 
-def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None, comp_width=None, timers=None):
+def _exchange_and_search_pipelined(dist, engine, table, bit, group, bin_size, bins, hist_all, sums_all, lo, hi):
+    """Plan X with the exchange hidden behind the search: the table is summed slice by slice (slice = one bucket of the
+    key partition = a contiguous run of canonical rows) on a side stream while the main stream searches the slices that
+    have already arrived — search(slice i) only reads table rows of slice i, and only canonical ones (no mirror needed).
+    CPU tensors (gloo tests): the same order of operations, sequentially."""
+    import torch
+    n_slices = engine.n_slices(lo, hi)
+    canon = table.view(-1, 2, 1 << bit)[:, 0, :]          # [entries / 2^(bit+1), 2^bit] canonical rows
+    buf = canon.contiguous()
+    rows = lambda i: tuple(k >> (bit + 1) for k in engine.slice_keys(i))
+    if not table.is_cuda:
+        for i in range(n_slices):
+            r0, r1 = rows(i)
+            dist.all_reduce(buf[r0:r1], group=group)
+            canon[r0:r1].copy_(buf[r0:r1])
+            if hi > lo:
+                engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
+        return
+    main = torch.cuda.current_stream()
+    comm = _side_stream(table.device)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    comm.wait_event(ready)
+    group_of, ahead = 2, 2                                # slices per all-reduce call; exchanges enqueued ahead of the search
+    starts = list(range(0, n_slices, group_of))
+    events = []
+    # the host alternates between the two streams so that the first search is enqueued as soon as two exchanges are
+    for step in range(len(starts) + ahead):
+        if step < len(starts):
+            i0, i1 = starts[step], min(starts[step] + group_of, n_slices)
+            r0, r1 = rows(i0)[0], rows(i1 - 1)[1]
+            with torch.cuda.stream(comm):
+                work = dist.all_reduce(buf[r0:r1], group=group, async_op=True)
+                work.wait()                               # the side stream waits; the host does not
+                canon[r0:r1].copy_(buf[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            events.append(ev)
+        done = step - ahead
+        if done >= 0:
+            main.wait_event(events[done])
+            if hi > lo:
+                for i in range(starts[done], min(starts[done] + group_of, n_slices)):
+                    engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
+    buf.record_stream(comm)
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    import torch
+    key = (device.type, device.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
+def exchange_group(world, max_ctas=None):
+    """A second NCCL communicator for the pipelined table exchange, limited to a few CTAs: the exchange only has to keep
+    pace with the search it hides behind (2 GiB in ~23 ms), and every SM NCCL does not occupy keeps searching.
+    Returns None when the backend cannot be configured (gloo, old torch): the default group is used then."""
+    import torch.distributed as dist
+    if max_ctas is None:   # measured at N = 2 (r01 notes in DESIGN.md): neither a CTA limit nor stream priority helps; off unless asked for
+        max_ctas = int(os.environ.get("LRB_XCHG_CTAS", "0"))
+    try:
+        if dist.get_backend() != "nccl" or max_ctas <= 0:
+            return None
+        opts = dist.ProcessGroupNCCL.Options()
+        # the search CTAs are persistent for a whole bucket: a high-priority NCCL stream gets its CTAs in at the next
+        # kernel boundary instead of queueing behind every search kernel already launched
+        opts.is_high_priority_stream = os.environ.get("LRB_XCHG_PRIO", "0") != "0"
+        opts.config.max_ctas = max_ctas
+        opts.config.min_ctas = 1
+        return dist.new_group(ranks=list(range(world)), backend="nccl", pg_options=opts)
+    except Exception:
+        return None
+
+
+def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None, comp_width=None, timers=None,
+                        pipeline_exchange=True, xgroup=None, feed=None, on_comp=None):
     """Runs the whole stage across the ranks of `group`.  Returns dict(comp, hist, sums, own=(lo, hi), table):
     comp/hist/sums hold the rows of this rank's own reads (row i <-> read own_lo + i)."""
     import torch.distributed as dist
@@ -135,8 +252,11 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
     mark = timers.mark if timers else (lambda name: None)
 
     # composition: read-sharded, no exchange.  Rows are written at their global index; return the own slice.
+    # feed (plan X only): [(read_lo_j, read_hi_j, wait_j)] — this rank's reads arrive in chunks; wait_j() orders the
+    # current stream after chunk j's arrival.  Composition and the key partition then run chunk by chunk.
+    fed = feed is not None and plan == "readshard_ar" and hasattr(engine, "count_fed") and hi > lo
     comp_all = engine.zeros((n, P))
-    if hi > lo:
+    if hi > lo and not fed:
         engine.composition(k, comp_all, lo, hi)
     comp = comp_all[lo:hi]
     mark("composition")
@@ -145,11 +265,28 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
         table = engine.zeros((entries,))
     else:
         table.zero_()
+    pipelined = plan == "readshard_ar" and pipeline_exchange and hasattr(engine, "search_slice") and getattr(engine, "canon_bit", None) is not None
     if plan == "readshard_ar":
-        if hi > lo:
+        if fed:
+            def per_chunk(j):
+                feed[j][2]()
+                engine.composition(k, comp_all, feed[j][0], feed[j][1])
+            engine.count_fed(table, lo, hi, [(a, b) for a, b, _ in feed], per_chunk)
+        elif hi > lo:
             engine.count(table, 0, entries, lo, hi)
         mark("count")
+        if on_comp is not None:      # the composition rows are final: the caller may start taking them home
+            on_comp(comp)
         bit = getattr(engine, "canon_bit", None)
+        if pipelined:
+            hist_all = engine.zeros((n, bins))
+            sums_all = engine.zeros((n,))
+            _exchange_and_search_pipelined(dist, engine, table, bit, xgroup if xgroup is not None else group, bin_size, bins,
+                                           hist_all, sums_all, lo, hi)
+            mark("exchange_table+search")
+            engine.mirror(table)
+            mark("mirror")
+            return {"comp": comp, "hist": hist_all[lo:hi], "sums": sums_all[lo:hi], "own": (lo, hi), "table": table}
         if bit is not None:
             _all_reduce_canonical_half(dist, table, bit, group)  # 2 GiB u32 sum over NVLink
         else:
@@ -220,6 +357,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     n, L = spec.n_reads, spec.total_bases
     eng = CudaEngine(dr, workspace_entries=int(L / world * 1.25) + (1 << 20))
     table = torch.zeros(TABLE_ENTRIES, dtype=torch.int32, device=dev)
+    xg = exchange_group(world)
 
     def timed(plan, steps):
         dist.barrier()
@@ -229,7 +367,8 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         tm = None
         for _ in range(steps):
             tm = _EventTimers(torch)
-            res = profile_distributed(eng, k, bs, bc, plan, table=table, timers=tm)
+            res = profile_distributed(eng, k, bs, bc, plan.split("/")[0], table=table, timers=tm, pipeline_exchange=not plan.endswith("/unpipelined"),
+                                      xgroup=xg)
         b.record()
         dist.barrier()
         torch.cuda.synchronize()
@@ -238,7 +377,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         return float(ms.item()), res, tm.phases_ms()
 
     plan_ms, checks = {}, {}
-    for plan in PLANS:
+    for plan in PLANS + ("readshard_ar/unpipelined",):
         timed(plan, 1)                                   # warm-up (NCCL channels, allocator)
         plan_ms[plan], res, _ = timed(plan, max(1, args.warmup - 1))
         tot = torch.stack([res["sums"].to(torch.int64).sum(), res["hist"].to(torch.int64).sum(), res["comp"].to(torch.int64).sum()])
@@ -255,7 +394,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     nbk = eng.ws.part.n_buckets
     # composition + 4 partition kernels (step hist, two scans, partition) + per-bucket count and search kernels + row sums
     # (+ mirror; plan B partitions twice)
-    launches = {"keyshard_rs": 6 + 2 * nbk, "keyshard_ag": 11 + 2 * nbk, "readshard_ar": 7 + 2 * nbk}[best] * args.steps
+    launches = {"keyshard_rs": 6 + 2 * nbk, "keyshard_ag": 11 + 2 * nbk, "readshard_ar": 7 + 2 * nbk}[best.split("/")[0]] * args.steps
 
     # e2e: every step also moves this rank's inputs host->device and its result rows device->host
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -266,7 +405,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     exc_blk, exc_word = layout.exceptions()
     h_exc = [pin(torch.from_numpy(a.view(np.int32))).copy_(torch.from_numpy(a.view(np.int32))) for a in (exc_blk, exc_word)]
     d_exc = [torch.empty(len(exc_blk), dtype=torch.int32, device=dev) for _ in range(2)]
-    if best == "readshard_ar":   # only the own shard's blocks are needed on this rank
+    if best.startswith("readshard_ar"):   # only the own shard's blocks are needed on this rank
         lo, hi = own_range(n, world, rank)
         rb = layout.read_blk
         b0, b1 = int(rb[lo]), int(rb[hi])
@@ -274,14 +413,61 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         b0, b1 = 0, layout.n_blocks
     out_h = {kk: pin(res[kk]) for kk in ("comp", "hist", "sums")}
 
+    # chunk plan of this rank's blocks (cut at read boundaries) for the pipelined plan-X step
+    rb = np.asarray(layout.read_blk)
+    if best.startswith("readshard_ar"):
+        n_ch = 16
+        cr = [lo] + [max(lo, min(hi, int(np.searchsorted(rb, b0 + (b1 - b0) * j // n_ch, side="right")) - 1)) for j in range(1, n_ch)] + [hi]
+        cr = sorted(set(cr))
+    else:
+        cr = None
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
     def e2e_step():
-        dr.codes[2 * b0:2 * b1].copy_(h_codes[2 * b0:2 * b1], non_blocking=True)
-        for d, h in zip(d_exc, h_exc):
-            d.copy_(h, non_blocking=True)
+        main = torch.cuda.current_stream()
+        if cr is None or len(cr) < 2:          # key-sharded plans need every read on every rank before anything starts
+            dr.codes[2 * b0:2 * b1].copy_(h_codes[2 * b0:2 * b1], non_blocking=True)
+            for d, h in zip(d_exc, h_exc):
+                d.copy_(h, non_blocking=True)
+            dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
+            r = profile_distributed(eng, k, bs, bc, best.split("/")[0], table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg)
+            for kk in out_h:
+                out_h[kk].copy_(r[kk], non_blocking=True)
+            return
+        # plan X: H2D in chunks on a copy stream; composition + key partition of chunk j run while chunk j+1 is on PCIe;
+        # the composition rows go home on a second copy stream while the table passes run
+        start = torch.cuda.Event()
+        start.record(main)
+        copy_in.wait_event(start)              # the previous step's kernels are done with the buffers
+        copy_out.wait_event(start)
+        evs = []
+        with torch.cuda.stream(copy_in):
+            for d, h in zip(d_exc, h_exc):
+                d.copy_(h, non_blocking=True)
+            ev0 = torch.cuda.Event()
+            ev0.record(copy_in)
+            for j in range(len(cr) - 1):
+                w0, w1 = 2 * int(rb[cr[j]]), 2 * int(rb[cr[j + 1]])
+                dr.codes[w0:w1].copy_(h_codes[w0:w1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_in)
+                evs.append(ev)
+        main.wait_event(ev0)
         dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
-        r = profile_distributed(eng, k, bs, bc, best, table=table)
-        for kk in out_h:
+        feed = [(cr[j], cr[j + 1], (lambda j=j: main.wait_event(evs[j]))) for j in range(len(cr) - 1)]
+
+        def comp_home(comp):
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(ready)
+                out_h["comp"].copy_(comp, non_blocking=True)
+
+        r = profile_distributed(eng, k, bs, bc, "readshard_ar", table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg,
+                                feed=feed, on_comp=comp_home)
+        for kk in ("hist", "sums"):
             out_h[kk].copy_(r[kk], non_blocking=True)
+        main.wait_stream(copy_out)
 
     e2e_step()
     dist.barrier()
@@ -301,7 +487,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
 
     count_ms = phases.get("count", 0.0)
     own_updates = valid_windows / world
-    alg = 0.375 * L * (1.0 if best != "readshard_ar" else 1.0 / world) + 16 * own_updates
+    alg = 0.375 * L * (1.0 if not best.startswith("readshard_ar") else 1.0 / world) + 16 * own_updates
     line = {"metric": metric, "value": L / ms_step / 1e6, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",

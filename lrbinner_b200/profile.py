@@ -332,12 +332,15 @@ class PartitionWorkspace:
         check(lib.lrb_dev_partition_check(C.byref(self.part), C.byref(needed), _stream()))
         return int(needed.value)
 
-    def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None, smem_count=True):
-        """smem_count: count through the second-level, shared-memory path (falls back per bucket on key skew)."""
+    def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None, smem_count=True,
+              bucket_lo=0, bucket_hi=None):
+        """smem_count: count through the second-level, shared-memory path (falls back per bucket on key skew).
+        bucket_lo/bucket_hi: only these buckets (sums are rewritten by the call that includes the last one)."""
         mode = (1 if count else 0) | (2 if search else 0) | (4 if (count and smem_count) else 0)
-        check(lib.lrb_dev_partition_apply(C.byref(self.part), mode, C.c_void_p(table.data_ptr()), bin_size, bins,
-                                          C.c_void_p(hist.data_ptr()) if hist is not None else None,
-                                          C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream()))
+        check(lib.lrb_dev_partition_apply_range(C.byref(self.part), mode, bucket_lo, 64 if bucket_hi is None else bucket_hi,
+                                                C.c_void_p(table.data_ptr()), bin_size, bins,
+                                                C.c_void_p(hist.data_ptr()) if hist is not None else None,
+                                                C.c_void_p(sums.data_ptr()) if sums is not None else None, _stream()))
 
 
 def dev_table15_partitioned(dr, ws, table, do_count=True, bin_size=1, bins=1, hist=None, sums=None, blk_lo=0, blk_hi=None,

@@ -73,6 +73,25 @@ class OracleEngine:
                 sums[i] += int(m)
 
 
+    def count_fed(self, table, lo, hi, chunks, per_chunk):
+        for j, (a, b) in enumerate(chunks):
+            per_chunk(j)
+            self.count(table, 0, self.table_entries, a, b)
+
+    # slice-wise search: plan X pipelines the table exchange with it (4 key slices here, 64 buckets in CudaEngine)
+    N_SLICES = 4
+
+    def n_slices(self, lo, hi):
+        return self.N_SLICES
+
+    def slice_keys(self, i):
+        w = self.table_entries // self.N_SLICES
+        return i * w, (i + 1) * w
+
+    def search_slice(self, table, bs, bc, hist, sums, lo, hi, i):
+        self.search(table, bs, bc, hist, sums, lo, hi, *self.slice_keys(i))
+
+
 def _worker(rank, world, port, plan, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -83,7 +102,16 @@ def _worker(rank, world, port, plan, q):
     seqs, _ = oracle.load_reads(os.path.join(GOLDEN, "g06_community.fa"))
     seqs = seqs[:41]                                   # odd count: exercises the padded last chunk
     eng = OracleEngine(seqs)
-    res = lrb_dist.profile_distributed(eng, K, BS, BC, plan)
+    simple = plan.endswith("/unpipelined")
+    feed = None
+    if plan.endswith("/fed"):      # this rank's reads arrive in three chunks (the e2e pipeline); the waits are no-ops on the CPU
+        lo, hi = lrb_dist.own_range(len(seqs), world, rank)
+        cuts = sorted({lo, lo + (hi - lo) // 3, lo + (hi - lo) // 2, hi})
+        arrived = []
+        feed = [(a, b, (lambda j=j: arrived.append(j))) for j, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]
+    res = lrb_dist.profile_distributed(eng, K, BS, BC, plan.split("/")[0], pipeline_exchange=not simple, feed=feed)
+    if feed is not None:
+        assert arrived == list(range(len(feed)))
     lo, hi = res["own"]
     q.put((rank, lo, hi, res["comp"].numpy().copy(), res["hist"].numpy().copy(), res["sums"].numpy().copy()))
     dist.barrier()
@@ -98,7 +126,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("plan", ["keyshard_rs", "keyshard_ag", "readshard_ar"])
+@pytest.mark.parametrize("plan", ["keyshard_rs", "keyshard_ag", "readshard_ar", "readshard_ar/unpipelined", "readshard_ar/fed"])
 def test_two_rank_plans_match_single_process_oracle(plan):
     from oracle import oracle
     world = 2
