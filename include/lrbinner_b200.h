@@ -106,6 +106,14 @@ int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_t blk_lo, u
                   uint32_t key_lo, uint32_t key_hi, void* stream);
 int lrb_dev_mirror(uint32_t* table, void* stream);
 
+/* Multi-GPU table exchange helpers (the reference has no counterpart: it is single-process).
+ * lrb_dev_copy2d: pitched device-to-device copy on the copy engines; src may be a peer GPU's table mapped into this
+ * process (rows of 2^15 bit-15-clear entries, pitch 2^16 entries).  lrb_dev_add_planes: dst rows (pitched) += the sum of
+ * n_planes staged copies of those rows (contiguous planes of rows x width_words); 16-byte aligned. */
+int lrb_dev_copy2d(void* dst, uint64_t dpitch, const void* src, uint64_t spitch, uint64_t width_bytes, uint64_t height, void* stream);
+int lrb_dev_add_planes(uint32_t* dst, uint64_t dst_pitch_words, const uint32_t* src, uint64_t plane_words, int n_planes,
+                       uint32_t width_words, uint32_t rows, void* stream);
+
 /* valid[] of `dev` from the read lengths alone (all in-read slots valid, padding slots invalid), then
  * valid[exc_blk[i]] = exc_valid[i] for the n_exc exception blocks (device arrays; may be NULL when n_exc == 0). */
 int lrb_dev_fill_valid(const lrb_reads_view* dev, const uint32_t* exc_blk, const uint32_t* exc_valid, uint64_t n_exc,

@@ -69,6 +69,8 @@ _SIG = {
     "lrb_dev_composition": (C.c_int, [C.POINTER(ReadsView), C.c_int, _P, C.c_uint64, C.c_uint64, _P]),
     "lrb_dev_count": (C.c_int, [C.POINTER(ReadsView), _P, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_mirror": (C.c_int, [_P, _P]),
+    "lrb_dev_copy2d": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_uint64, C.c_uint64, _P]),
+    "lrb_dev_add_planes": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_search": (C.c_int, [C.POINTER(ReadsView), _P, C.c_long, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
                                  C.c_uint32, C.c_uint32, _P]),
     "lrb_dev_fill_blk_read": (C.c_int, [C.POINTER(ReadsView), _P, _P]),

@@ -10,6 +10,7 @@
 //   * mirror : 64x64 tiled "transpose" T[x] = T[rc(x)] for bit-15-set x (coalesced both ways).
 // No tensor cores anywhere: nothing here is a dense contraction (BASELINE.json north_star).
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -351,6 +352,45 @@ extern "C" int lrb_dev_mirror(uint32_t* table, void* stream) {
     if (!table) return lrb_set_error(LRB_EINVAL, "lrb_dev_mirror: null table");
     k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table);
     LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+// ---- multi-GPU table exchange helpers (lrbinner_b200/dist.py: PeerExchange) -----------------------------------------
+// dst rows (pitched) += sum of n_planes staged copies of the same rows (contiguous planes): 16-byte accesses, one pass.
+__global__ void __launch_bounds__(256)
+k_add_planes(uint4* __restrict__ dst, uint64_t dst_pitch4, const uint4* __restrict__ src, uint64_t plane4, int n_planes, uint32_t width4,
+             uint64_t total4) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / width4, c = i - r * width4;
+        uint4 acc = dst[r * dst_pitch4 + c];
+        for (int p = 0; p < n_planes; ++p) {
+            const uint4 v = __ldcs(src + (uint64_t)p * plane4 + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        dst[r * dst_pitch4 + c] = acc;
+    }
+}
+
+extern "C" int lrb_dev_add_planes(uint32_t* dst, uint64_t dst_pitch_words, const uint32_t* src, uint64_t plane_words, int n_planes,
+                                  uint32_t width_words, uint32_t rows, void* stream) {
+    if (!dst || !src) return lrb_set_error(LRB_EINVAL, "lrb_dev_add_planes: null argument");
+    if ((width_words & 3u) || (dst_pitch_words & 3u) || (plane_words & 3u) || ((uintptr_t)dst & 15u) || ((uintptr_t)src & 15u))
+        return lrb_set_error(LRB_EINVAL, "lrb_dev_add_planes: rows, pitches and pointers must be 16-byte aligned");
+    if (!rows || !width_words || n_planes <= 0) return LRB_OK;
+    const uint64_t total4 = (uint64_t)rows * (width_words / 4);
+    const unsigned grid = (unsigned)std::min<uint64_t>((total4 + 255) / 256, 148ull * 16);
+    k_add_planes<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), dst_pitch_words / 4, reinterpret_cast<const uint4*>(src),
+                                                         plane_words / 4, n_planes, width_words / 4, total4);
+    LRB_CUDA(cudaGetLastError());
+    return LRB_OK;
+}
+
+// pitched device-to-device copy on the copy engines (src may be a peer's memory mapped into this process)
+extern "C" int lrb_dev_copy2d(void* dst, uint64_t dpitch, const void* src, uint64_t spitch, uint64_t width_bytes, uint64_t height,
+                              void* stream) {
+    if (!dst || !src) return lrb_set_error(LRB_EINVAL, "lrb_dev_copy2d: null argument");
+    if (!width_bytes || !height) return LRB_OK;
+    LRB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return LRB_OK;
 }
 

@@ -120,6 +120,10 @@ class CudaEngine:
     def mirror(self, table):
         self.p.dev_mirror(table)
 
+    def mirror_on(self, table, stream):
+        with self.torch.cuda.stream(stream):
+            self.p.dev_mirror(table)
+
     def search(self, table, bin_size, bins, hist, sums, read_lo, read_hi, key_lo, key_hi):
         self._partition(read_lo, read_hi, key_lo, key_hi, count=False)   # re-used from count() when the rectangle is the same
         self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums)
@@ -204,6 +208,81 @@ def _exchange_and_search_pipelined(dist, engine, table, bit, group, bin_size, bi
     buf.record_stream(comm)
 
 
+class PeerExchange:
+    """Table exchange of plan X over NVLink peer memory, driven by the copy engines (no SM is taken from the search).
+
+    Every rank's table lives in symmetric memory (torch symmetric memory: the same allocation mapped into every rank
+    of the node).  Piece by piece (a piece = `group_of` buckets of the key partition = a run of canonical rows) a side
+    stream PULLS the piece's rows straight out of every peer's table with pitched device-to-device copies
+    (lrb_dev_copy2d: the copy engines move them through NVSwitch) into a staging buffer, passes a device-side barrier
+    (every rank has taken its copy of the piece, so the rows may now change), and adds the staged rows to its own
+    (lrb_dev_add_planes): the sum is then complete for those rows on this rank.  The main stream only waits for the
+    piece's event and searches its buckets, so the exchange runs ahead of the search and hides behind it; the mirror
+    pass (it writes only the non-canonical half, which the search never reads) follows the last piece on the side stream.
+    Traffic per rank: (N-1) x 2 GiB in.  NCCL's all-reduce moves less (2 (N-1)/N x 2 GiB) but with SM-resident kernels,
+    and pipelining it slice by slice hid only 2 of its 6.4 ms at N = 2 (profiles/r01_bench_n2_*.json)."""
+
+    def __init__(self, device, bit=15, entries=TABLE_ENTRIES, group_of=4, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.torch, self.dist, self.lib, self.check = torch, dist, _lib.lib, _lib.check
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.bit, self.rows, self.cols, self.group_of = bit, entries >> (bit + 1), 1 << bit, group_of
+        self.table = symm.empty(entries, dtype=torch.int32, device=device)       # THE table of this rank
+        self.hdl = symm.rendezvous(self.table, group=self.group)
+        self.peers = [(self.rank + d) % self.world for d in range(1, self.world)]  # rotated: no two ranks start on the same peer
+        self.peer_table = {p: self.hdl.get_buffer(p, (entries,), torch.int32) for p in self.peers}
+        self.stage = None
+        self.comm = torch.cuda.Stream(device=device)
+
+    def run(self, engine, table, bin_size, bins, hist_all, sums_all, lo, hi):
+        """table (== self.table) holds this rank's private canonical counts; on return it holds the global, mirrored table
+        and hist_all / sums_all the coverage rows of the reads [lo, hi)."""
+        import ctypes as C
+        torch = self.torch
+        assert table.data_ptr() == self.table.data_ptr(), "PeerExchange: the table must be the symmetric-memory one (self.table)"
+        n_slices = engine.n_slices(lo, hi)
+        rows = lambda i: tuple(k >> (self.bit + 1) for k in engine.slice_keys(i))
+        starts = list(range(0, n_slices, self.group_of))
+        span = [(rows(s)[0], rows(min(s + self.group_of, n_slices) - 1)[1]) for s in starts]
+        piece_rows = max(r1 - r0 for r0, r1 in span)
+        n_peers = len(self.peers)
+        if self.stage is None or self.stage.shape[2] < piece_rows:
+            self.stage = torch.empty((2, n_peers, piece_rows, self.cols), dtype=torch.int32, device=table.device)
+        main, comm = torch.cuda.current_stream(), self.comm
+        st = C.c_void_p(comm.cuda_stream)
+        row_bytes, pitch_bytes = 4 * self.cols, 8 * self.cols
+        ready = torch.cuda.Event()
+        ready.record(main)
+        comm.wait_event(ready)
+        events = []
+        with torch.cuda.stream(comm):
+            self.hdl.barrier()                                # every rank has counted
+            for g, (r0, r1) in enumerate(span):
+                slot = self.stage[g & 1]
+                for j, p in enumerate(self.peers):
+                    self.check(self.lib.lrb_dev_copy2d(C.c_void_p(slot[j].data_ptr()), row_bytes,
+                                                       C.c_void_p(self.peer_table[p].data_ptr() + r0 * pitch_bytes), pitch_bytes,
+                                                       row_bytes, r1 - r0, st))
+                self.hdl.barrier()                            # every rank has its copies of this piece: the rows may change now
+                self.check(self.lib.lrb_dev_add_planes(C.c_void_p(table.data_ptr() + r0 * pitch_bytes), 2 * self.cols,
+                                                       C.c_void_p(slot.data_ptr()), piece_rows * self.cols, n_peers, self.cols, r1 - r0, st))
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                events.append(ev)
+            engine.mirror_on(table, comm)                     # non-canonical half: never read by the search
+            self.hdl.barrier()                                # (the next step refills the tables only after everybody is here)
+        for g, ev in enumerate(events):
+            main.wait_event(ev)
+            if hi > lo:
+                for i in range(starts[g], min(starts[g] + self.group_of, n_slices)):
+                    engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
+        main.wait_stream(comm)
+
+
 _SIDE = {}
 
 
@@ -237,7 +316,7 @@ def exchange_group(world, max_ctas=None):
 
 
 def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None, comp_width=None, timers=None,
-                        pipeline_exchange=True, xgroup=None, feed=None, on_comp=None):
+                        pipeline_exchange=True, xgroup=None, feed=None, on_comp=None, peer_exchange=None):
     """Runs the whole stage across the ranks of `group`.  Returns dict(comp, hist, sums, own=(lo, hi), table):
     comp/hist/sums hold the rows of this rank's own reads (row i <-> read own_lo + i)."""
     import torch.distributed as dist
@@ -281,8 +360,13 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
         if pipelined:
             hist_all = engine.zeros((n, bins))
             sums_all = engine.zeros((n,))
-            _exchange_and_search_pipelined(dist, engine, table, bit, xgroup if xgroup is not None else group, bin_size, bins,
-                                           hist_all, sums_all, lo, hi)
+            if peer_exchange is not None:
+                peer_exchange.run(engine, table, bin_size, bins, hist_all, sums_all, lo, hi)   # leaves the table mirrored
+                mark("exchange_table+search+mirror")
+                return {"comp": comp, "hist": hist_all[lo:hi], "sums": sums_all[lo:hi], "own": (lo, hi), "table": table}
+            else:
+                _exchange_and_search_pipelined(dist, engine, table, bit, xgroup if xgroup is not None else group, bin_size, bins,
+                                               hist_all, sums_all, lo, hi)
             mark("exchange_table+search")
             engine.mirror(table)
             mark("mirror")
@@ -358,6 +442,19 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     eng = CudaEngine(dr, workspace_entries=int(L / world * 1.25) + (1 << 20))
     table = torch.zeros(TABLE_ENTRIES, dtype=torch.int32, device=dev)
     xg = exchange_group(world)
+    px = None
+    try:                                                  # copy-engine exchange over peer memory (needs symmetric memory on this node)
+        px = PeerExchange(dev)
+    except Exception as ex:
+        if rank == 0:
+            print(f"[lrb] peer-memory exchange unavailable ({ex!r}); NCCL exchange only", file=__import__("sys").stderr)
+    ok = torch.tensor([1 if px is not None else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not int(ok.item()):
+        px = None
+    if px is not None:
+        del table
+        table = px.table                                  # one 4 GiB table per rank, in symmetric memory (all plans use it)
 
     def timed(plan, steps):
         dist.barrier()
@@ -368,7 +465,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         for _ in range(steps):
             tm = _EventTimers(torch)
             res = profile_distributed(eng, k, bs, bc, plan.split("/")[0], table=table, timers=tm, pipeline_exchange=not plan.endswith("/unpipelined"),
-                                      xgroup=xg)
+                                      xgroup=xg, peer_exchange=px if plan.endswith("/p2p") else None)
         b.record()
         dist.barrier()
         torch.cuda.synchronize()
@@ -377,7 +474,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         return float(ms.item()), res, tm.phases_ms()
 
     plan_ms, checks = {}, {}
-    for plan in PLANS + ("readshard_ar/unpipelined",):
+    for plan in PLANS + ("readshard_ar/unpipelined",) + (("readshard_ar/p2p",) if px is not None else ()):
         timed(plan, 1)                                   # warm-up (NCCL channels, allocator)
         plan_ms[plan], res, _ = timed(plan, max(1, args.warmup - 1))
         tot = torch.stack([res["sums"].to(torch.int64).sum(), res["hist"].to(torch.int64).sum(), res["comp"].to(torch.int64).sum()])
@@ -430,7 +527,8 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
             for d, h in zip(d_exc, h_exc):
                 d.copy_(h, non_blocking=True)
             dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
-            r = profile_distributed(eng, k, bs, bc, best.split("/")[0], table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg)
+            r = profile_distributed(eng, k, bs, bc, best.split("/")[0], table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg,
+                                    peer_exchange=px if best.endswith("/p2p") else None)
             for kk in out_h:
                 out_h[kk].copy_(r[kk], non_blocking=True)
             return
@@ -464,7 +562,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
                 out_h["comp"].copy_(comp, non_blocking=True)
 
         r = profile_distributed(eng, k, bs, bc, "readshard_ar", table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg,
-                                feed=feed, on_comp=comp_home)
+                                feed=feed, on_comp=comp_home, peer_exchange=px if best.endswith("/p2p") else None)
         for kk in ("hist", "sums"):
             out_h[kk].copy_(r[kk], non_blocking=True)
         main.wait_stream(copy_out)

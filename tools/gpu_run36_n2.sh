@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+LRB_XCHG_DEBUG=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"
+grep "xchg timeline" gpurun_out/bench_n2.err | tail -2
