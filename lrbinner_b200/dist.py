@@ -102,11 +102,21 @@ class CudaEngine:
         per_chunk(j) is called before chunk j is touched (it makes the stream wait for the chunk and may run other
         per-chunk work, e.g. the composition)."""
         rect = (read_lo, read_hi, 0, self.table_entries)
+        dbg = os.environ.get("LRB_FEED_DEBUG") == "1"
+        tl = []
+        def stamp(name):
+            if dbg:
+                e = self.torch.cuda.Event(enable_timing=True)
+                e.record()
+                tl.append((name, e))
+        stamp("begin")
         self.ws.begin(True, 0, self.table_entries, self.shift, count=True)
         for j, (rlo, rhi) in enumerate(chunks):
             per_chunk(j)
+            stamp(f"c{j}")
             blo, bhi = self._blocks(rlo, rhi)
             self.ws.add(blo, bhi)
+            stamp(f"a{j}")
         if rect not in self._verified:               # first time for this rectangle: verify the workspace (synchronises)
             try:
                 self.ws.check()
@@ -116,6 +126,12 @@ class CudaEngine:
             self._verified.add(rect)
         self._rect = rect
         self.ws.apply(table, count=True)
+        stamp("applied")
+        if dbg:
+            self.torch.cuda.synchronize()
+            import sys
+            print("[feed timeline ms] " + " ".join(f"{nm}={tl[0][1].elapsed_time(e):.1f}" for nm, e in tl) +
+                  f" chunks={[(a, b, self._blocks(a, b)) for a, b in chunks][:3]}", file=sys.stderr, flush=True)
 
     def mirror(self, table):
         self.p.dev_mirror(table)
@@ -212,17 +228,15 @@ class PeerExchange:
     """Table exchange of plan X over NVLink peer memory, driven by the copy engines (no SM is taken from the search).
 
     Every rank's table lives in symmetric memory (torch symmetric memory: the same allocation mapped into every rank
-    of the node).  Piece by piece (a piece = `group_of` buckets of the key partition = a run of canonical rows) a side
-    stream PULLS the piece's rows straight out of every peer's table with pitched device-to-device copies
-    (lrb_dev_copy2d: the copy engines move them through NVSwitch) into a staging buffer, passes a device-side barrier
-    (every rank has taken its copy of the piece, so the rows may now change), and adds the staged rows to its own
-    (lrb_dev_add_planes): the sum is then complete for those rows on this rank.  The main stream only waits for the
-    piece's event and searches its buckets, so the exchange runs ahead of the search and hides behind it; the mirror
-    pass (it writes only the non-canonical half, which the search never reads) follows the last piece on the side stream.
-    Traffic per rank: (N-1) x 2 GiB in.  NCCL's all-reduce moves less (2 (N-1)/N x 2 GiB) but with SM-resident kernels,
-    and pipelining it slice by slice hid only 2 of its 6.4 ms at N = 2 (profiles/r01_bench_n2_*.json)."""
+    of the node).  A side stream moves rows of the canonical half between the tables with pitched device-to-device
+    copies (lrb_dev_copy2d: the copy engines carry them through NVSwitch), orders the ranks with device-side barriers
+    and adds pulled rows with lrb_dev_add_planes (see run()).  The main stream only waits for a round's event and
+    searches its buckets, so the exchange runs ahead of the search and hides behind it; the mirror pass (it writes
+    only the non-canonical half, which the search never reads) follows the last round on the side stream.
+    NCCL's all-reduce moves the same bytes with SM-resident kernels; pipelining it slice by slice hid only 2 of its
+    6.4 ms at N = 2 and left 13 ms exposed at N = 8 (profiles/r01_bench_n2_*.json, r01_bench_n8_*.json)."""
 
-    def __init__(self, device, bit=15, entries=TABLE_ENTRIES, group_of=4, group=None):
+    def __init__(self, device, bit=15, entries=TABLE_ENTRIES, group_of=0, group=None):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -240,46 +254,67 @@ class PeerExchange:
 
     def run(self, engine, table, bin_size, bins, hist_all, sums_all, lo, hi):
         """table (== self.table) holds this rank's private canonical counts; on return it holds the global, mirrored table
-        and hist_all / sums_all the coverage rows of the reads [lo, hi)."""
+        and hist_all / sums_all the coverage rows of the reads [lo, hi).
+
+        Reduce-scatter + all-gather by hand, round by round.  The canonical rows are cut into pieces (a run of buckets);
+        round k handles the pieces k N .. k N + N - 1, piece g owned by rank g mod N:
+          A  the owner pulls the piece's rows out of every peer's table (their private counts) and adds them to its own;
+             device barrier (all sums of the round are final);
+          B  every rank pulls the other N - 1 finished pieces of the round from their owners over its own rows.
+        Then the round's buckets are searched on the main stream while the side stream is rounds ahead.  Per rank
+        2 (N-1)/N x 2 GiB come in over NVLink, every byte by copy engine."""
         import ctypes as C
         torch = self.torch
         assert table.data_ptr() == self.table.data_ptr(), "PeerExchange: the table must be the symmetric-memory one (self.table)"
         n_slices = engine.n_slices(lo, hi)
+        W, me = self.world, self.rank
         rows = lambda i: tuple(k >> (self.bit + 1) for k in engine.slice_keys(i))
-        starts = list(range(0, n_slices, self.group_of))
-        span = [(rows(s)[0], rows(min(s + self.group_of, n_slices) - 1)[1]) for s in starts]
+        group_of = self.group_of if self.group_of else max(1, n_slices // (8 * W))      # ~8 rounds
+        starts = list(range(0, n_slices, group_of))
+        span = [(rows(s)[0], rows(min(s + group_of, n_slices) - 1)[1]) for s in starts]
+        G = len(span)
+        n_rounds = (G + W - 1) // W
         piece_rows = max(r1 - r0 for r0, r1 in span)
         n_peers = len(self.peers)
-        if self.stage is None or self.stage.shape[2] < piece_rows:
-            self.stage = torch.empty((2, n_peers, piece_rows, self.cols), dtype=torch.int32, device=table.device)
+        if self.stage is None or self.stage.shape[1] < piece_rows:
+            self.stage = torch.empty((n_peers, piece_rows, self.cols), dtype=torch.int32, device=table.device)
         main, comm = torch.cuda.current_stream(), self.comm
         st = C.c_void_p(comm.cuda_stream)
         row_bytes, pitch_bytes = 4 * self.cols, 8 * self.cols
+        my_rows = lambda r0: C.c_void_p(table.data_ptr() + r0 * pitch_bytes)
+        peer_rows = lambda p, r0: C.c_void_p(self.peer_table[p].data_ptr() + r0 * pitch_bytes)
         ready = torch.cuda.Event()
         ready.record(main)
         comm.wait_event(ready)
         events = []
         with torch.cuda.stream(comm):
             self.hdl.barrier()                                # every rank has counted
-            for g, (r0, r1) in enumerate(span):
-                slot = self.stage[g & 1]
-                for j, p in enumerate(self.peers):
-                    self.check(self.lib.lrb_dev_copy2d(C.c_void_p(slot[j].data_ptr()), row_bytes,
-                                                       C.c_void_p(self.peer_table[p].data_ptr() + r0 * pitch_bytes), pitch_bytes,
-                                                       row_bytes, r1 - r0, st))
-                self.hdl.barrier()                            # every rank has its copies of this piece: the rows may change now
-                self.check(self.lib.lrb_dev_add_planes(C.c_void_p(table.data_ptr() + r0 * pitch_bytes), 2 * self.cols,
-                                                       C.c_void_p(slot.data_ptr()), piece_rows * self.cols, n_peers, self.cols, r1 - r0, st))
+            for k in range(n_rounds):
+                g = k * W + me
+                if g < G:                                     # A: complete the sum of my piece of this round
+                    r0, r1 = span[g]
+                    for j, p in enumerate(self.peers):
+                        self.check(self.lib.lrb_dev_copy2d(C.c_void_p(self.stage[j].data_ptr()), row_bytes, peer_rows(p, r0), pitch_bytes,
+                                                           row_bytes, r1 - r0, st))
+                    self.check(self.lib.lrb_dev_add_planes(my_rows(r0), 2 * self.cols, C.c_void_p(self.stage.data_ptr()),
+                                                           piece_rows * self.cols, n_peers, self.cols, r1 - r0, st))
+                self.hdl.barrier()                            # the sums of this round are final everywhere
+                for p in self.peers:                          # B: the other pieces of the round, from their owners
+                    g = k * W + p
+                    if g < G:
+                        r0, r1 = span[g]
+                        self.check(self.lib.lrb_dev_copy2d(my_rows(r0), pitch_bytes, peer_rows(p, r0), pitch_bytes, row_bytes, r1 - r0, st))
                 ev = torch.cuda.Event()
                 ev.record(comm)
                 events.append(ev)
             engine.mirror_on(table, comm)                     # non-canonical half: never read by the search
             self.hdl.barrier()                                # (the next step refills the tables only after everybody is here)
-        for g, ev in enumerate(events):
+        for k, ev in enumerate(events):
             main.wait_event(ev)
             if hi > lo:
-                for i in range(starts[g], min(starts[g] + self.group_of, n_slices)):
-                    engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
+                for g in range(k * W, min((k + 1) * W, G)):
+                    for i in range(starts[g], min(starts[g] + group_of, n_slices)):
+                        engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
         main.wait_stream(comm)
 
 
@@ -496,7 +531,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     # e2e: every step also moves this rank's inputs host->device and its result rows device->host
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     dr.download_into(layout)
-    h_codes = torch.from_numpy(layout.codes.view(np.int32))
+    h_codes = torch.from_numpy(layout.codes.view(np.int32))   # whole global set; page-locked only if the host allowed that much
     # validity crosses PCIe as the exception list only (0 entries for pure-ACGT reads); the bitmap is rebuilt on the device
     layout.index_valid(threads=os.cpu_count() or 8)
     exc_blk, exc_word = layout.exceptions()
@@ -508,6 +543,14 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         b0, b1 = int(rb[lo]), int(rb[hi])
     else:
         b0, b1 = 0, layout.n_blocks
+    if best.startswith("readshard_ar") and world > 1:
+        # this rank ships only its own shard: give that a page-locked buffer of its own (8 ranks x the global set would
+        # ask the host for more pinned memory than it grants, and the copies would silently go through pageable staging)
+        own = pin(h_codes[2 * b0:2 * b1])
+        own.copy_(h_codes[2 * b0:2 * b1])
+        h_own, own_w0 = own, 2 * b0
+    else:
+        h_own, own_w0 = h_codes, 0
     out_h = {kk: pin(res[kk]) for kk in ("comp", "hist", "sums")}
 
     # chunk plan of this rank's blocks (cut at read boundaries) for the pipelined plan-X step
@@ -519,6 +562,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     else:
         cr = None
     copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    marks = {}
 
     def e2e_step():
         main = torch.cuda.current_stream()
@@ -534,8 +578,9 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
             return
         # plan X: H2D in chunks on a copy stream; composition + key partition of chunk j run while chunk j+1 is on PCIe;
         # the composition rows go home on a second copy stream while the table passes run
-        start = torch.cuda.Event()
+        start = torch.cuda.Event(enable_timing=True)
         start.record(main)
+        marks["start"] = start
         copy_in.wait_event(start)              # the previous step's kernels are done with the buffers
         copy_out.wait_event(start)
         evs = []
@@ -546,10 +591,11 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
             ev0.record(copy_in)
             for j in range(len(cr) - 1):
                 w0, w1 = 2 * int(rb[cr[j]]), 2 * int(rb[cr[j + 1]])
-                dr.codes[w0:w1].copy_(h_codes[w0:w1], non_blocking=True)
-                ev = torch.cuda.Event()
+                dr.codes[w0:w1].copy_(h_own[w0 - own_w0:w1 - own_w0], non_blocking=True)
+                ev = torch.cuda.Event(enable_timing=(j == len(cr) - 2))
                 ev.record(copy_in)
                 evs.append(ev)
+            marks["h2d"] = evs[-1]
         main.wait_event(ev0)
         dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
         feed = [(cr[j], cr[j + 1], (lambda j=j: main.wait_event(evs[j]))) for j in range(len(cr) - 1)]
@@ -561,11 +607,16 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
                 copy_out.wait_event(ready)
                 out_h["comp"].copy_(comp, non_blocking=True)
 
+        marks["tm"] = _EventTimers(torch)
         r = profile_distributed(eng, k, bs, bc, "readshard_ar", table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg,
-                                feed=feed, on_comp=comp_home, peer_exchange=px if best.endswith("/p2p") else None)
+                                feed=feed, on_comp=comp_home, peer_exchange=px if best.endswith("/p2p") else None, timers=marks["tm"])
+        marks["compute"] = torch.cuda.Event(enable_timing=True)
+        marks["compute"].record(main)
         for kk in ("hist", "sums"):
             out_h[kk].copy_(r[kk], non_blocking=True)
         main.wait_stream(copy_out)
+        marks["end"] = torch.cuda.Event(enable_timing=True)
+        marks["end"].record(main)
 
     e2e_step()
     dist.barrier()
@@ -580,6 +631,9 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     e2e_ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
+    e2e_phases = {kk: marks["start"].elapsed_time(marks[kk]) for kk in ("h2d", "compute", "end")} if "end" in marks else None
+    if e2e_phases is not None:
+        e2e_phases["phases"] = marks["tm"].phases_ms()
     h2d = 4 * (2 * (b1 - b0)) + 8 * len(exc_blk)
     d2h = sum(int(t.numel()) * 4 for t in out_h.values())
 
@@ -593,7 +647,8 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
                        "k": k, "bin_size": bs, "bins": bc, "plan": best, "plan_ms": plan_ms, "valid_15mer_windows": valid_windows,
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": L / e2e_ms / 1e6, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "note": "per-rank bytes; max-over-ranks time"},
+                    "ms_per_step": e2e_ms, "note": "per-rank bytes; max-over-ranks time",
+                    "rank0_ms_since_step_start": e2e_phases},
             "gpu_launches": launches,
             "roofline": {"kernel": "count phase on rank 0 (partition + k2_partition + k_count_smem per bucket)", "bound": "hbm", "achieved": alg / max(count_ms, 1e-6) / 1e6 / 1.0 if count_ms else None,
                          "peak": hbm_peak, "unit": "GB/s", "frac": (alg / max(count_ms, 1e-6) / 1e6) / hbm_peak if count_ms else None,
