@@ -432,6 +432,52 @@ def test_second_level_count_survives_key_skew():
     assert 1 <= fell_back[24] <= 32, fell_back
 
 
+def test_multi_gpu_exchange_building_blocks_on_one_device():
+    """The pieces of dist.PeerExchange on one GPU: two read shards counted into two private tables ("ranks"), the peer's
+    canonical rows pulled piece by piece with lrb_dev_copy2d into a staging plane, added with lrb_dev_add_planes, and every
+    piece's buckets searched right after its sum (lrb_dev_partition_apply_range) — equals one count + one search over
+    all reads."""
+    spec = SynthSpec(5000, seed=41, n_rate=1e-4, edge_lengths=True, scale=0.05)
+    pr = spec.host_packed()
+    dr = DeviceReads(pr, DEV)
+    n, bs, bc = pr.n_reads, 32, 10
+    z = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=DEV)
+    whole, hist_w, sums_w = z(2 ** 30), z(n, bc), z(n)
+    ws = PartitionWorkspace(dr)
+    dev_table15_partitioned(dr, ws, whole, True, bs, bc, hist_w, sums_w)
+    blk = np.array(pr.read_blk)
+    cut = n // 2
+    mine, peer = z(2 ** 30), z(2 ** 30)
+    dev_table15_partitioned(dr, ws, peer, True, blk_lo=int(blk[cut]), blk_hi=pr.n_blocks)        # the peer's shard
+    ws.build(True, 0, int(blk[cut]))                                                             # my shard: count ...
+    ws.apply(mine, count=True)
+    rows, cols = 2 ** 14, 2 ** 15                                                                # canonical rows: pitch 2^16 entries
+    piece = rows // 16
+    stage = torch.full((1, piece, cols), -1, dtype=torch.int32, device=DEV)
+    hist_p, sums_p = z(n, bc), z(n)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nb = ws.part.n_buckets
+    for g in range(16):                                                                          # ... then exchange + search piece by piece
+        r0 = g * piece
+        _lib.check(_lib.lib.lrb_dev_copy2d(C.c_void_p(stage.data_ptr()), 4 * cols, C.c_void_p(peer.data_ptr() + r0 * 8 * cols), 8 * cols,
+                                           4 * cols, piece, st))
+        _lib.check(_lib.lib.lrb_dev_add_planes(C.c_void_p(mine.data_ptr() + r0 * 8 * cols), 2 * cols, C.c_void_p(stage.data_ptr()),
+                                               piece * cols, 1, cols, piece, st))
+        ws.apply(mine, count=False, search=True, bin_size=bs, bins=bc, hist=hist_p, sums=sums_p,
+                 bucket_lo=g * nb // 16, bucket_hi=(g + 1) * nb // 16)
+    assert torch.equal(mine, whole)                                                              # canonical half summed, other half still zero
+    # my shard's rows are complete (the peer's reads were not in my partition): rows of reads < cut match the full search
+    assert torch.equal(hist_p[:cut], hist_w[:cut]) and torch.equal(sums_p[:cut], sums_w[:cut])
+    assert int(hist_p[cut:].sum().item()) == 0
+    # several planes at once (N - 1 = 3 peers), odd row count
+    acc = torch.arange(5 * 2 * cols, dtype=torch.int32, device=DEV).reshape(5, 2, cols).contiguous()
+    planes = torch.randint(0, 2 ** 31 - 1, (3, 8, cols), dtype=torch.int32, device=DEV)          # plane stride = 8 rows, 5 used
+    want = acc.clone()
+    want[:, 0, :] += planes[:, :5].sum(dim=0, dtype=torch.int32)
+    _lib.check(_lib.lib.lrb_dev_add_planes(C.c_void_p(acc.data_ptr()), 2 * cols, C.c_void_p(planes.data_ptr()), 8 * cols, 3, cols, 5, st))
+    assert torch.equal(acc, want)
+
+
 # ---- full-size properties (BASELINE.json configs) ---------------------------------------------------------
 
 def _full_size_properties(name, subsample=200):
