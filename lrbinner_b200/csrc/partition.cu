@@ -332,8 +332,10 @@ __device__ __forceinline__ uint32_t entry_key(uint32_t e, uint32_t bucket_base, 
 }
 
 __global__ void __launch_bounds__(256)
-k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, uint32_t bucket_base,
-             uint32_t hi_mask2, uint32_t* __restrict__ table, int fallback_only) {
+k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket0, int n_chunks, uint32_t bucket_base0,
+             int shift, uint32_t hi_mask2, uint32_t* __restrict__ table, int fallback_only) {
+    const int bucket = bucket0 + (int)blockIdx.y;   // one launch may cover several buckets (gridDim.y)
+    const uint32_t bucket_base = bucket_base0 + ((uint32_t)blockIdx.y << shift);
     if (meta->overflow) return;
     if (fallback_only && !meta->overflow2[bucket]) return;  // the shared-memory path counted this bucket
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -585,10 +587,12 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
 
 // one CTA per sub-slice: its segments -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
 __global__ void __launch_bounds__(1024)
-k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta, int bucket, L2Layout Y, uint32_t bucket_base,
+k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta, int bucket0, L2Layout Y, uint32_t bucket_base0, int shift,
              uint32_t* __restrict__ table) {
     extern __shared__ uint32_t s_tab[];  // 2^15
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, sub = blockIdx.x;
+    const int bucket = bucket0 + (int)blockIdx.y;   // one launch may cover several buckets (gridDim.y): no 1.7-wave tail per bucket
+    const uint32_t bucket_base = bucket_base0 + ((uint32_t)blockIdx.y << shift);
     if (meta->overflow || meta->overflow2[bucket]) return;
     const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + (Y.strided ? Y.fill_pos(sub) : sub);  // + cta * nb * nsub
     const size_t fill_stride = (size_t)Y.nb * Y.nsub;
@@ -658,9 +662,13 @@ constexpr uint32_t kBinLut = 2048;  // counts below this go through a shared-mem
 
 template <bool USE_LUT, int U>
 __global__ void __launch_bounds__(256)
-k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket, int n_chunks, ChunkList L,
-              StepTables T, uint32_t bucket_base, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
+k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket0, int n_chunks, ChunkList L,
+              StepTables T, uint32_t bucket_base0, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
               uint64_t magic, uint32_t B, uint32_t* __restrict__ hist) {
+    // one launch may cover several buckets (gridDim.y): CTAs are dispatched x-fastest, so the buckets are still worked on
+    // one after the other (their slices take turns in L2) but the tail of one overlaps the head of the next
+    const int bucket = bucket0 + (int)blockIdx.y;
+    const uint32_t bucket_base = bucket_base0 + ((uint32_t)blockIdx.y << shift);
     __shared__ uint32_t s_bnd[8][kTaskRuns + 1];  // per warp: start of each run of the span, [kTaskRuns] = end of the span
     __shared__ uint32_t s_r0[8][kTaskRuns];       // per warp: read index of each run's step relative to the span's first
     __shared__ uint16_t s_lut[USE_LUT ? kBinLut : 2];
@@ -1000,10 +1008,29 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     const bool unroll8 = !(un_env && atoi(un_env) == 4);
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
     if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
-    for (int b = bucket_lo; b < bucket_hi; ++b) {
+    const bool count_batched = do_count && smem_count && !do_search && bucket_hi > bucket_lo;
+    if (count_batched) {  // count only: every bucket in one launch each of the two kernels (the second only counts flagged buckets)
+        const uint32_t base0 = part->key_lo + ((uint32_t)bucket_lo << shift);
+        const dim3 g1(Y.nsub, (unsigned)(bucket_hi - bucket_lo)), g2(grid, (unsigned)(bucket_hi - bucket_lo));
+        k_count_smem<<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table);
+        k_count_keys<<<g2, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, base0, shift, hi_mask2, table, 1);
+    }
+    const bool search_batched = do_search && !do_count && bucket_hi > bucket_lo;
+    if (search_batched) {
+        const uint32_t base0 = part->key_lo + ((uint32_t)bucket_lo << shift);
+        const dim3 gs(sgrid, (unsigned)(bucket_hi - bucket_lo));
+#define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
+    k_search_keys<LUT, UN><<<gs, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, L, T, base0, hi_mask2, shift, table, S32, magic, \
+                                               (uint32_t)bins, hist)
+        if (use_lut) LRB_LAUNCH_SEARCH(true, 4);
+        else if (unroll8) LRB_LAUNCH_SEARCH(false, 8);
+        else LRB_LAUNCH_SEARCH(false, 4);
+#undef LRB_LAUNCH_SEARCH
+    }
+    for (int b = bucket_lo; b < bucket_hi && !count_batched && !search_batched; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
-        if (smem_count) k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, table);
-        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, hi_mask2, table, smem_count ? 1 : 0);
+        if (smem_count) k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table);
+        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, shift, hi_mask2, table, smem_count ? 1 : 0);
         if (do_search) {
 #define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
     k_search_keys<LUT, UN><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \

@@ -152,9 +152,11 @@ class CudaEngine:
     def slice_keys(self, i):
         return i << self.ws.part.shift, (i + 1) << self.ws.part.shift
 
-    def search_slice(self, table, bin_size, bins, hist, sums, read_lo, read_hi, i):
+    def search_slice(self, table, bin_size, bins, hist, sums, read_lo, read_hi, i, i_end=None):
+        """slices [i, i_end) in one launch (default: slice i alone)"""
         self._partition(read_lo, read_hi, 0, self.table_entries, count=False)
-        self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums, bucket_lo=i, bucket_hi=i + 1)
+        self.ws.apply(table, count=False, search=True, bin_size=bin_size, bins=bins, hist=hist, sums=sums, bucket_lo=i,
+                      bucket_hi=i + 1 if i_end is None else i_end)
 
 
 def _reduce_scatter(dist, out, inp, group):
@@ -219,8 +221,7 @@ def _exchange_and_search_pipelined(dist, engine, table, bit, group, bin_size, bi
         if done >= 0:
             main.wait_event(events[done])
             if hi > lo:
-                for i in range(starts[done], min(starts[done] + group_of, n_slices)):
-                    engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
+                engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, starts[done], min(starts[done] + group_of, n_slices))
     buf.record_stream(comm)
 
 
@@ -311,10 +312,9 @@ class PeerExchange:
             self.hdl.barrier()                                # (the next step refills the tables only after everybody is here)
         for k, ev in enumerate(events):
             main.wait_event(ev)
-            if hi > lo:
-                for g in range(k * W, min((k + 1) * W, G)):
-                    for i in range(starts[g], min(starts[g] + group_of, n_slices)):
-                        engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, i)
+            if hi > lo:                                       # the round's buckets are contiguous: one launch
+                g0, g1 = k * W, min((k + 1) * W, G)
+                engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, starts[g0], min(starts[g1 - 1] + group_of, n_slices))
         main.wait_stream(comm)
 
 

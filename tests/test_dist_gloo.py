@@ -88,8 +88,9 @@ class OracleEngine:
         w = self.table_entries // self.N_SLICES
         return i * w, (i + 1) * w
 
-    def search_slice(self, table, bs, bc, hist, sums, lo, hi, i):
-        self.search(table, bs, bc, hist, sums, lo, hi, *self.slice_keys(i))
+    def search_slice(self, table, bs, bc, hist, sums, lo, hi, i, i_end=None):
+        for j in range(i, i + 1 if i_end is None else i_end):
+            self.search(table, bs, bc, hist, sums, lo, hi, *self.slice_keys(j))
 
 
 def _worker(rank, world, port, plan, q):
