@@ -547,6 +547,10 @@ def test_full_size_properties_config2_headline():
     _full_size_properties("cfg2_1M_5kb_ont_k4", subsample=100)
 
 
+def test_full_size_properties_config3_10gbp():
+    _full_size_properties("cfg3_2M_5kb_k3", subsample=40)
+
+
 def test_full_size_properties_config4_hifi_k5():
     _full_size_properties("cfg4_500k_15kb_hifi_k5", subsample=40)
 
