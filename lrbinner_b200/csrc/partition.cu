@@ -407,7 +407,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     constexpr uint32_t nsub = 1u << LOG2_NSUB, sub_mask = nsub - 1u;   // == Y.nsub
     constexpr uint32_t cap = (uint32_t)kL2Stage / nsub, cap_shift = 15u - LOG2_NSUB;
-    constexpr uint32_t spw = nsub / kL2Warps;      // sub-slices owned by a warp: warp * spw + j, j < spw (nsub >= 16)
+    constexpr uint32_t spw = nsub / kL2Warps;      // sub-slices (staging rows) owned by a warp (nsub >= 16)
     if (meta->overflow) return;  // lists incomplete: nothing is applied anywhere
     uint32_t* __restrict__ fill = reinterpret_cast<uint32_t*>(ws) + (size_t)blockIdx.x * Y.nb * nsub;  // this CTA's row
     for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) s_cnt[i] = 0;
@@ -479,7 +479,9 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         }
     };
     const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
-    const uint32_t my_sub = STRIDED ? warp + (uint32_t)kL2Warps * lane : warp * spw + lane;  // lane j < spw looks after the fill counter of this sub-slice (contiguous: no bank conflicts)
+    // lane j < spw of a warp looks after row / fill counter j of the warp's sub-slices.  STRIDED (default): the warp owns
+    // sub-slices warp + 16 j — measured 2 ms faster per step than the blocked ownership 16 warp + j (LRB_K2_ROWS=block)
+    const uint32_t my_sub = STRIDED ? warp + (uint32_t)kL2Warps * lane : warp * spw + lane;
     const uint32_t my_pos = STRIDED ? Y.fill_pos(my_sub) : my_sub;   // its counter in the fill row
     uint32_t e[kL2PerThread];
     uint32_t n_cur = 0, n_next = 0, b_cur = 0, b_next = 0;
