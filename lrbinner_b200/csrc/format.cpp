@@ -54,46 +54,76 @@ extern "C" uint32_t lrb_fixed6(uint32_t num, uint32_t den, int coverage) { retur
 
 namespace {
 
+// two decimal digits at a time
+struct Digits2 {
+    char d[100][2];
+    Digits2() { for (int i = 0; i < 100; ++i) { d[i][0] = (char)('0' + i / 10); d[i][1] = (char)('0' + i % 10); } }
+};
+const Digits2 kDigits2;
+
 inline void put_fixed6(char* dst, uint32_t q) {  // 8 chars "d.dddddd"
-    dst[0] = (char)('0' + q / 1000000u);
+    if (q == 0) { memcpy(dst, "0.000000", 8); return; }   // most composition / coverage cells
+    const uint32_t ip = q / 1000000u, f = q - ip * 1000000u;
+    const uint32_t a = f / 10000u, r = f - a * 10000u, b2 = r / 100u, c2 = r - b2 * 100u;
+    dst[0] = (char)('0' + ip);
     dst[1] = '.';
-    uint32_t f = q % 1000000u;
-    for (int i = 7; i >= 2; --i) { dst[i] = (char)('0' + f % 10u); f /= 10u; }
+    memcpy(dst + 2, kDigits2.d[a], 2);
+    memcpy(dst + 4, kDigits2.d[b2], 2);
+    memcpy(dst + 6, kDigits2.d[c2], 2);
 }
 
 int comp_width(int k) { return k == 3 ? 32 : k == 4 ? 136 : k == 5 ? 512 : 0; }
 
-template <class F>
-void parallel_rows(uint64_t n, int threads, F f) {
-    if (threads < 1) threads = 1;
-    if (threads > 64) threads = 64;
-    if (n < 256) threads = 1;
-    if (threads == 1) { f(0, n); return; }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t) pool.emplace_back(f, n * t / threads, n * (t + 1) / threads);
-    for (auto& th : pool) th.join();
+bool pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
+    while (n) {
+        const ssize_t w = pwrite(fd, p, n, (off_t)off);
+        if (w <= 0) return false;
+        p += w;
+        n -= (size_t)w;
+        off += (uint64_t)w;
+    }
+    return true;
 }
 
-// rows are produced in chunks so the text never has to exist in memory as a whole
+// Fixed-width rows: every thread formats blocks of its share of the rows into a private buffer and writes them at their
+// final offset (pwrite), so neither the text nor the file copy is ever serial and nothing of file size sits in memory.
+// row(i, dst) fills row i (row_bytes bytes).
+template <class RowFn>
+int write_fixed_rows(const char* path, const void* head, size_t head_bytes, uint64_t n_rows, size_t row_bytes, int threads, RowFn row) {
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return lrb_set_error(LRB_EIO, "cannot open %s for writing", path);
+    bool ok = !head_bytes || pwrite_all(fd, (const char*)head, head_bytes, 0);
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (n_rows < 256) threads = 1;
+    const uint64_t block_rows = std::max<uint64_t>(1, (2ull << 20) / std::max<size_t>(row_bytes, 1));
+    std::vector<char> failed((size_t)threads, 0);
+    auto work = [&](int t) {
+        const uint64_t a = n_rows * (uint64_t)t / (uint64_t)threads, b = n_rows * (uint64_t)(t + 1) / (uint64_t)threads;
+        std::vector<char> buf((size_t)std::min<uint64_t>(block_rows, std::max<uint64_t>(b - a, 1)) * row_bytes);
+        for (uint64_t lo = a; lo < b; lo += block_rows) {
+            const uint64_t hi = std::min(b, lo + block_rows);
+            for (uint64_t i = lo; i < hi; ++i) row(i, buf.data() + (size_t)(i - lo) * row_bytes);
+            if (!pwrite_all(fd, buf.data(), (size_t)(hi - lo) * row_bytes, head_bytes + lo * row_bytes)) { failed[(size_t)t] = 1; return; }
+        }
+    };
+    if (ok && n_rows) {
+        if (threads == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; ++t) pool.emplace_back(work, t);
+            for (auto& th : pool) th.join();
+        }
+        for (char f : failed) ok = ok && !f;
+    }
+    if (close(fd) != 0) ok = false;
+    if (!ok) return lrb_set_error(LRB_EIO, "short write to %s", path);
+    return LRB_OK;
+}
+
 template <class RowFn>
 int write_rows(const char* path, uint64_t n_rows, size_t row_bytes, int threads, RowFn row) {
-    FILE* f = fopen(path, "wb");
-    if (!f) return lrb_set_error(LRB_EIO, "cannot open %s for writing", path);
-    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / std::max<size_t>(row_bytes, 1));
-    std::vector<char> buf;
-    for (uint64_t lo = 0; lo < n_rows; lo += chunk_rows) {
-        const uint64_t hi = std::min(n_rows, lo + chunk_rows);
-        buf.resize((size_t)(hi - lo) * row_bytes);
-        parallel_rows(hi - lo, threads, [&](uint64_t a, uint64_t b) {
-            for (uint64_t i = a; i < b; ++i) row(lo + i, buf.data() + (size_t)i * row_bytes);
-        });
-        if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
-            fclose(f);
-            return lrb_set_error(LRB_EIO, "short write to %s", path);
-        }
-    }
-    if (fclose(f) != 0) return lrb_set_error(LRB_EIO, "close failed for %s", path);
-    return LRB_OK;
+    return write_fixed_rows(path, nullptr, 0, n_rows, row_bytes, threads, row);
 }
 
 std::string npy_header(uint64_t rows, uint64_t cols) {
@@ -115,22 +145,9 @@ std::string npy_header(uint64_t rows, uint64_t cols) {
 
 template <class RowFn>
 int write_npy(const char* path, uint64_t n_rows, uint64_t cols, int threads, RowFn row) {
-    FILE* f = fopen(path, "wb");
-    if (!f) return lrb_set_error(LRB_EIO, "cannot open %s for writing", path);
     const std::string h = npy_header(n_rows, cols);
-    if (fwrite(h.data(), 1, h.size(), f) != h.size()) { fclose(f); return lrb_set_error(LRB_EIO, "short write to %s", path); }
-    const uint64_t chunk_rows = std::max<uint64_t>(1, (64ull << 20) / (cols * 8));
-    std::vector<double> buf;
-    for (uint64_t lo = 0; lo < n_rows; lo += chunk_rows) {
-        const uint64_t hi = std::min(n_rows, lo + chunk_rows);
-        buf.resize((size_t)((hi - lo) * cols));
-        parallel_rows(hi - lo, threads, [&](uint64_t a, uint64_t b) {
-            for (uint64_t i = a; i < b; ++i) row(lo + i, buf.data() + (size_t)(i * cols));
-        });
-        if (fwrite(buf.data(), 8, buf.size(), f) != buf.size()) { fclose(f); return lrb_set_error(LRB_EIO, "short write to %s", path); }
-    }
-    if (fclose(f) != 0) return lrb_set_error(LRB_EIO, "close failed for %s", path);
-    return LRB_OK;
+    return write_fixed_rows(path, h.data(), h.size(), n_rows, (size_t)cols * 8, threads,
+                            [&](uint64_t i, char* dst) { row(i, reinterpret_cast<double*>(dst)); });
 }
 
 inline uint32_t comp_total(uint32_t len, int k) { return len >= (uint32_t)k ? len - (uint32_t)k + 1u : 0u; }
