@@ -394,6 +394,42 @@ def test_npy_writers_equal_float_of_text(tmp_path):
         assert got.dtype == np.float64 and got.shape == (n, width) and np.array_equal(got, want)
 
 
+def test_writers_are_thread_count_invariant_and_match_printf(tmp_path):
+    """Multi-threaded writers (blocks written at their final offset): any thread count gives the same bytes, and the
+    bytes are C's "%f" of the double quotient (count-kmers.cpp:110-118, search-15mers.cpp:35-48)."""
+    rng = np.random.default_rng(9)
+    n, k, P, bins = 5000, 4, 136, 10
+    rl = rng.integers(0, 30000, size=n).astype(np.uint32)
+    comp = np.zeros((n, P), dtype=np.uint32)
+    for i in range(n):
+        tot = max(int(rl[i]) - k + 1, 0)
+        if tot:
+            comp[i] = rng.multinomial(tot, rng.dirichlet(np.ones(P) * 0.2))
+    sums = rng.integers(0, 30000, size=n).astype(np.uint32)
+    hist = np.zeros((n, bins), dtype=np.uint32)
+    for i in range(n):
+        if sums[i]:
+            hist[i] = rng.multinomial(int(sums[i]), rng.dirichlet(np.ones(bins) * 0.3))
+    for kind, args, in (("composition", (_p(comp), _p(rl), n, k)), ("coverage", (_p(hist), _p(sums), n, bins))):
+        blobs = {}
+        for ext in ("txt", "npy"):
+            for th in (1, 3, 8):
+                path = str(tmp_path / f"{kind}.{th}.{ext}")
+                assert getattr(_lib.lib, f"lrb_write_{kind}_{ext}")(path.encode(), *args, th) == 0
+                blobs[(ext, th)] = open(path, "rb").read()
+            assert blobs[(ext, 1)] == blobs[(ext, 3)] == blobs[(ext, 8)], (kind, ext)
+        lines = blobs[("txt", 1)].split(b"\n")
+        assert len(lines) == n + 1 and lines[-1] == b""
+        for i in rng.choice(n, size=200, replace=False):
+            if kind == "composition":
+                tot = max(1.0, float(max(int(rl[i]) - k + 1, 0)))
+                want = b"".join(b"%f " % (float(c) / tot) for c in comp[i])
+            else:
+                vals = [float(c) / float(sums[i]) if sums[i] else 0.0 for c in hist[i]]
+                want = b" ".join(b"%f" % (0.0 if v < 1e-4 else v) for v in vals)
+            assert lines[i] == want, (kind, i)
+
+
 def test_table_file_roundtrip_format(tmp_path):
     t = np.zeros(2 ** 30, dtype=np.uint32)
     t[[0, 5, 2 ** 30 - 1]] = [7, 9, 11]
