@@ -526,7 +526,13 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     nbk = eng.ws.part.n_buckets
     # composition + 4 partition kernels (step hist, two scans, partition) + per-bucket count and search kernels + row sums
     # (+ mirror; plan B partitions twice)
-    launches = {"keyshard_rs": 6 + 2 * nbk, "keyshard_ag": 11 + 2 * nbk, "readshard_ar": 7 + 2 * nbk}[best.split("/")[0]] * args.steps
+    # our kernels per step: composition + per chunk (step_hist, group_scan, chunk_scan, partition, k2_partition) + count
+    # (k_count_smem, k_count_keys: one launch each over all buckets) + search launches + k_row_sums + mirror
+    # (+ lrb_dev_add_planes per round of the peer exchange; plan B partitions twice)
+    nch = max(1, eng.ws.part.n_chunks)
+    base = 1 + 5 * nch + 2 + 1 + 1
+    launches = {"keyshard_rs": base + 1, "keyshard_ag": base + 4 * nch + 1, "readshard_ar": base + nbk // 2,
+                "readshard_ar/unpipelined": base + 1, "readshard_ar/p2p": base + 2 * 8}[best] * args.steps
 
     # e2e: every step also moves this rank's inputs host->device and its result rows device->host
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
