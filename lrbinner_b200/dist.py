@@ -225,6 +225,19 @@ def _exchange_and_search_pipelined(dist, engine, table, bit, group, bin_size, bi
     buf.record_stream(comm)
 
 
+def exchange_schedule(n_slices, world, group_of=0):
+    """Pieces and rounds of the peer-memory exchange.  Returns (pieces, rounds): pieces[g] = (first_slice, end_slice),
+    consecutive and covering [0, n_slices); rounds[k] = [(g, owner), ...] with owner = g mod world — the piece that rank
+    completes in step A of round k; in step B every rank fetches the round's other pieces from their owners.
+    group_of = 0 picks the piece size that gives about 8 rounds."""
+    if group_of <= 0:
+        group_of = max(1, n_slices // (8 * world))
+    pieces = [(s, min(s + group_of, n_slices)) for s in range(0, n_slices, group_of)]
+    rounds = [[(g, g % world) for g in range(k * world, min((k + 1) * world, len(pieces)))]
+              for k in range((len(pieces) + world - 1) // world)]
+    return pieces, rounds
+
+
 class PeerExchange:
     """Table exchange of plan X over NVLink peer memory, driven by the copy engines (no SM is taken from the search).
 
@@ -270,11 +283,9 @@ class PeerExchange:
         n_slices = engine.n_slices(lo, hi)
         W, me = self.world, self.rank
         rows = lambda i: tuple(k >> (self.bit + 1) for k in engine.slice_keys(i))
-        group_of = self.group_of if self.group_of else max(1, n_slices // (8 * W))      # ~8 rounds
-        starts = list(range(0, n_slices, group_of))
-        span = [(rows(s)[0], rows(min(s + group_of, n_slices) - 1)[1]) for s in starts]
-        G = len(span)
-        n_rounds = (G + W - 1) // W
+        pieces, rounds = exchange_schedule(n_slices, W, self.group_of)
+        span = [(rows(a)[0], rows(b - 1)[1]) for a, b in pieces]      # canonical rows of every piece
+        G, n_rounds = len(pieces), len(rounds)
         piece_rows = max(r1 - r0 for r0, r1 in span)
         n_peers = len(self.peers)
         if self.stage is None or self.stage.shape[1] < piece_rows:
@@ -313,8 +324,7 @@ class PeerExchange:
         for k, ev in enumerate(events):
             main.wait_event(ev)
             if hi > lo:                                       # the round's buckets are contiguous: one launch
-                g0, g1 = k * W, min((k + 1) * W, G)
-                engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, starts[g0], min(starts[g1 - 1] + group_of, n_slices))
+                engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, pieces[rounds[k][0][0]][0], pieces[rounds[k][-1][0]][1])
         main.wait_stream(comm)
 
 

@@ -167,3 +167,22 @@ def test_shard_arithmetic():
     for w in (1, 2, 4, 8):
         ks = [d.key_range(w, r) for r in range(w)]
         assert ks[0][0] == 0 and ks[-1][1] == 2 ** 30 == d.TABLE_ENTRIES and all(a[1] == b[0] for a, b in zip(ks, ks[1:]))
+
+
+def test_peer_exchange_schedule_covers_every_slice_once():
+    from lrbinner_b200 import dist as d
+    for n_slices in (1, 4, 16, 63, 64):
+        for world in (1, 2, 3, 4, 5, 7, 8):
+            for group_of in (0, 1, 3):
+                pieces, rounds = d.exchange_schedule(n_slices, world, group_of)
+                assert pieces[0][0] == 0 and pieces[-1][1] == n_slices and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+                seen = [g for rnd in rounds for g, _ in rnd]
+                assert seen == list(range(len(pieces)))                      # every piece in exactly one round, in order
+                for rnd in rounds:
+                    owners = [o for _, o in rnd]
+                    assert len(set(owners)) == len(owners) and all(o == g % world for g, o in rnd)   # one piece per rank and round
+                    assert [g for g, _ in rnd] == list(range(rnd[0][0], rnd[0][0] + len(rnd)))      # contiguous: one search launch
+    pieces, rounds = d.exchange_schedule(64, 8)
+    assert len(rounds) == 8 and all(b - a == 1 for a, b in pieces)            # 8 GPUs: 8 rounds of 8 single-bucket pieces
+    pieces, rounds = d.exchange_schedule(64, 2)
+    assert len(rounds) == 8 and all(b - a == 4 for a, b in pieces)
