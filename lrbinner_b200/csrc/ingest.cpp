@@ -56,6 +56,7 @@ struct Parsed {
 static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t limit, Parsed& out, bool* ended) {
     int pending = 0;  // header char already consumed
     std::string qual;
+    bool reserved = false;
     *ended = false;
     while (true) {
         size_t hdr;
@@ -104,7 +105,14 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
                 acc = len;
                 if (appended_rest && acc > 1 && buf[ls + acc - 1] == '\r') --acc;
             } else {
-                if (!multi) { out.pool.append((const char*)buf + first_off, acc); multi = true; }
+                if (!multi) {
+                    // first multi-line record of this range: the pool can never need more than the rest of the range, and
+                    // reserving that once (address space only) avoids the copy-on-grow of a 10^8-byte string
+                    // (0.43 -> 0.15 s per 200 MB of 80-column FASTA)
+                    if (!reserved) { out.pool.reserve(out.pool.size() + (std::min(limit, n) > hdr ? std::min(limit, n) - hdr : 0)); reserved = true; }
+                    out.pool.append((const char*)buf + first_off, acc);
+                    multi = true;
+                }
                 out.pool.append((const char*)buf + ls, len);
                 acc += len;
                 if (appended_rest && acc > 1 && out.pool.back() == '\r') { out.pool.pop_back(); --acc; }
@@ -223,12 +231,14 @@ struct FileImage {
     ~FileImage() { if (map) munmap(map, map_len); }
 };
 
-static bool read_gz(const char* path, std::vector<unsigned char>& data) {
+static bool read_gz(const char* path, std::vector<unsigned char>& data, uint64_t size_hint) {
     gzFile f = gzopen(path, "rb");
     if (!f) return false;
     gzbuffer(f, 1 << 20);
     size_t n = 0;
-    data.resize(1 << 22);
+    // size_hint: ISIZE of the (last) gzip member = its uncompressed size mod 2^32 — right for the usual single-member
+    // file below 4 GiB, and only a starting size otherwise (the buffer still doubles when it runs out)
+    data.resize(std::max<uint64_t>(size_hint + (1u << 20) + 1, 1u << 22));
     for (;;) {
         if (data.size() - n < (1 << 20)) data.resize(data.size() * 2);
         const size_t room = std::min<size_t>(data.size() - n, 1u << 30);
@@ -259,8 +269,15 @@ static void load_file(const char* path, FileImage& img) {
             return;
         }
     }
+    uint64_t hint = 0;
+    if (gz && st.st_size >= 18) {
+        unsigned char isize[4];
+        if (pread(fd, isize, 4, st.st_size - 4) == 4)
+            hint = (uint64_t)isize[0] | (uint64_t)isize[1] << 8 | (uint64_t)isize[2] << 16 | (uint64_t)isize[3] << 24;
+        if (hint < (uint64_t)st.st_size) hint = 0;   // wrapped around 2^32 (or not a plain single member): no use as a size
+    }
     close(fd);
-    if (read_gz(path, img.heap)) {
+    if (read_gz(path, img.heap, hint)) {
         img.data = img.heap.data();
         img.size = img.heap.size();
     }
