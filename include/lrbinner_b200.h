@@ -84,6 +84,9 @@ int lrb_reads_index_valid(lrb_reads* r, int threads, uint64_t* n_exceptions);
 /* The current exception list (host pointers owned by `r`; *n = 0 and NULLs when none was built):
  * valid[blk[i]] == word[i] != the word implied by the read length, blk ascending. */
 int lrb_reads_exceptions(const lrb_reads* r, const uint32_t** blk, const uint32_t** word, uint64_t* n);
+/* Reads [read_lo, read_hi) of `r` as a read set of its own (index arrays rebased to read 0 / block 0).  The packed stream
+ * is shared with `r`, which must outlive the slice.  This is how the host pipeline forms device shards and batches. */
+int lrb_reads_slice(const lrb_reads* r, uint64_t read_lo, uint64_t read_hi, lrb_reads** out);
 void lrb_reads_free(lrb_reads* r);
 
 /* ------------------------------------------------------------------------------------------------
@@ -230,6 +233,13 @@ int lrb_synth_host(const lrb_synth_params* p, const uint32_t* glen, const uint32
  * ---------------------------------------------------------------------------------------------- */
 typedef struct lrb_ctx lrb_ctx;
 int lrb_ctx_create(int device, lrb_ctx** out);
+/* One context driving n_devices GPUs from this process (devices[] = CUDA ordinals, NULL = 0..n-1).  devices[0] is
+ * the primary: it ends up with the complete table (lrb_ctx_table_save / _load act on it).  lrb_profile_host then shards
+ * the reads over the devices (contiguous ranges, so row i is still read i), every device counts its own reads into a
+ * private table, the tables are summed over NVLink peer memory by the copy engines, and every device searches its own
+ * reads: SURVEY.md 8(e) plan "read-sharded" — the one that won the three-way measurement. */
+int lrb_ctx_create_multi(const int* devices, int n_devices, lrb_ctx** out);
+int lrb_ctx_device_count(const lrb_ctx* ctx);
 void lrb_ctx_destroy(lrb_ctx* ctx);
 
 /* Whole profile stage for one read set held in (pinned) HOST memory:
@@ -237,9 +247,27 @@ void lrb_ctx_destroy(lrb_ctx* ctx);
  *   -> mirror -> D2H(results; composition rows return while the table passes run).
  * comp_counts[N*P] (P from k), cov_hist[N*bins], cov_sums[N] are HOST buffers (may be NULL to skip the
  * corresponding phase).  If table_host != NULL the 4 GiB table is copied back as well.
- * If use_loaded_table != 0 the count phase is skipped and the table already in the context is searched. */
+ * flags: LRB_PROFILE_USE_LOADED_TABLE — skip the count phase and search the table already in the context;
+ *        LRB_PROFILE_KEEP_TABLE — count even when neither the search nor table_host asks for it (lrb_ctx_table_save follows).
+ * Bounded device memory: a read set whose working set (8.6 B per base of lists beside the 4 GiB table) does not fit is
+ * processed in BATCHES — the table accumulates over the batches, then every batch is shipped and partitioned again for
+ * the search — with a one-line notice on stderr; results are identical (tests force this with LRB_BATCH_BASES).  This
+ * is the reference's constant-memory behaviour (count-15mers.cpp:75-99: reads stream through a bounded queue). */
+#define LRB_PROFILE_USE_LOADED_TABLE 1
+#define LRB_PROFILE_KEEP_TABLE 2
 int lrb_profile_host(lrb_ctx* ctx, const lrb_reads* reads, int k, long bin_size, int bins, uint32_t* comp_counts,
-                     uint32_t* cov_hist, uint32_t* cov_sums, uint32_t* table_host, int use_loaded_table);
+                     uint32_t* cov_hist, uint32_t* cov_sums, uint32_t* table_host, int flags);
+/* How the last lrb_profile_host call ran. */
+typedef struct {
+    int n_devices;            /* GPUs that took part */
+    int n_batches;            /* batches over all devices; == n_devices when everything stayed resident */
+    int table_path;           /* 0 direct kernels (LRB_TABLE_PATH=direct), 1 key-partitioned + L2 atomics, 2 + shared-memory count */
+    int lists_reused;         /* 1: the search re-used the lists the count built (single batch per device) */
+    float wall_ms;            /* host wall clock of the call */
+    float exchange_ms;        /* device 0: first to last operation of the table exchange (0 on one GPU) */
+    uint64_t batch_bases_max; /* slots of the largest batch */
+} lrb_run_info;
+int lrb_ctx_last_info(const lrb_ctx* ctx, lrb_run_info* info);
 /* Device milliseconds (CUDA events) of the last lrb_profile_host call.  The call is a 3-stream pipeline, so the
  * phases overlap: [0] H2D of the packed reads (copy stream) [1] composition + partition until the last chunk is
  * processed (runs beside [0]) [2] table passes (count + search per bucket) [3] mirror [4] direct search (only
@@ -284,6 +312,10 @@ int lrb_search_15mers(const char* table_path, const char* reads_path, const char
  * write_table) into out_dir/profiles/; write_npy additionally emits com_profs.npy / cov_profs.npy. */
 int lrb_profile(const char* reads_path, const char* out_dir, int k, long bin_size, int bins, int threads,
                 int write_table, int write_npy);
+/* The same on n_gpus GPUs of this node (devices LRB_DEVICE.. ; n_gpus <= 0: LRB_GPUS from the environment, default 1),
+ * byte-identical files.  The three tool drop-ins above and lrb_profile honour LRB_GPUS the same way. */
+int lrb_profile_multi(const char* reads_path, const char* out_dir, int k, long bin_size, int bins, int threads, int n_gpus,
+                      int write_table, int write_npy);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,15 @@ class Partition(C.Structure):
 PART_SMALL_U64 = 16384
 
 
+class RunInfo(C.Structure):
+    """lrb_run_info: how the last lrb_profile_host call ran."""
+    _fields_ = [("n_devices", C.c_int), ("n_batches", C.c_int), ("table_path", C.c_int), ("lists_reused", C.c_int),
+                ("wall_ms", C.c_float), ("exchange_ms", C.c_float), ("batch_bases_max", C.c_uint64)]
+
+
+PROFILE_USE_LOADED_TABLE, PROFILE_KEEP_TABLE = 1, 2
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_genomes", C.c_uint32), ("sub_thr", C.c_uint32), ("ins_thr", C.c_uint32),
                 ("del_thr", C.c_uint32), ("n_thr", C.c_uint32), ("read_base", C.c_uint64)]
@@ -62,6 +71,7 @@ _SIG = {
     "lrb_reads_from_lengths": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
     "lrb_reads_view_get": (C.c_int, [_P, C.POINTER(ReadsView)]),
     "lrb_reads_unpack": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "lrb_reads_slice": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.POINTER(_P)]),
     "lrb_reads_free": (None, [_P]),
     "lrb_reads_index_valid": (C.c_int, [_P, C.c_int, _P]),
     "lrb_reads_exceptions": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64)]),
@@ -89,7 +99,10 @@ _SIG = {
     "lrb_dev_synth": (C.c_int, [C.POINTER(ReadsView), C.POINTER(SynthParams), _P, _P, _P]),
     "lrb_synth_host": (C.c_int, [C.POINTER(SynthParams), _P, _P, _P, C.c_uint64, _P, _P]),
     "lrb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "lrb_ctx_create_multi": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "lrb_ctx_device_count": (C.c_int, [_P]),
     "lrb_ctx_destroy": (None, [_P]),
+    "lrb_ctx_last_info": (C.c_int, [_P, _P]),
     "lrb_profile_host": (C.c_int, [_P, _P, C.c_int, C.c_long, C.c_int, _P, _P, _P, _P, C.c_int]),
     "lrb_ctx_last_timings": (C.c_int, [_P, _P]),
     "lrb_pinned_alloc": (_P, [C.c_size_t]),
@@ -108,6 +121,7 @@ _SIG = {
     "lrb_count_15mers": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     "lrb_search_15mers": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_long, C.c_int, C.c_int]),
     "lrb_profile": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "lrb_profile_multi": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
 }
 
 EXPORTS = tuple(_SIG)

@@ -27,6 +27,7 @@ struct lrb_reads {
     uint32_t* tile_read = nullptr;  // n_tiles
     uint32_t* tile_blk = nullptr;   // n_tiles
     bool pinned = false;            // buffers came from cudaHostAlloc
+    bool borrowed = false;          // codes/valid point into another lrb_reads (lrb_reads_slice): not freed here
     // validity exceptions: blocks whose valid word differs from the one implied by the read length (all in-read
     // slots valid).  Lets the host path ship 0.25 B/base instead of 0.375: the device rebuilds `valid` from
     // read_len and patches these blocks (lrb_dev_fill_valid).

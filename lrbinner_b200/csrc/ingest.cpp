@@ -364,8 +364,10 @@ static void pack_read(const unsigned char* s, uint32_t len, uint32_t* codes, uin
 
 static void free_reads(lrb_reads* r) {
     if (!r) return;
-    lrb_host_free(r->codes, r->pinned);
-    lrb_host_free(r->valid, r->pinned);
+    if (!r->borrowed) {
+        lrb_host_free(r->codes, r->pinned);
+        lrb_host_free(r->valid, r->pinned);
+    }
     free(r->read_len);
     free(r->read_blk);
     free(r->tile_read);
@@ -605,6 +607,62 @@ extern "C" int lrb_reads_from_lengths(const uint32_t* lengths, uint64_t n_reads,
     if (n_reads) memcpy(r->read_len, lengths, sizeof(uint32_t) * n_reads);
     int rc = build_layout(r, true);
     if (rc) { free_reads(r); return rc; }
+    *out = r;
+    return LRB_OK;
+}
+
+// A contiguous run of reads as a read set of its own: index arrays rebased to block 0 / read 0, the packed stream
+// shared with the parent (a read always starts on a block boundary, so the sub-stream is a plain sub-array).
+extern "C" int lrb_reads_slice(const lrb_reads* p, uint64_t read_lo, uint64_t read_hi, lrb_reads** out) {
+    if (!p || !out) return lrb_set_error(LRB_EINVAL, "lrb_reads_slice: null argument");
+    *out = nullptr;
+    if (read_hi > p->n_reads) read_hi = p->n_reads;
+    if (read_lo > read_hi) read_lo = read_hi;
+    const uint64_t n = read_hi - read_lo;
+    const uint32_t b0 = p->read_blk[read_lo], b1 = p->read_blk[read_hi];
+    const uint64_t t0 = (uint64_t)(std::lower_bound(p->tile_read, p->tile_read + p->n_tiles, (uint32_t)read_lo) - p->tile_read);
+    const uint64_t t1 = (uint64_t)(std::lower_bound(p->tile_read, p->tile_read + p->n_tiles, (uint32_t)read_hi) - p->tile_read);
+    lrb_reads* r = new lrb_reads();
+    r->borrowed = true;
+    r->pinned = p->pinned;
+    r->n_reads = n;
+    r->n_blocks = b1 - b0;
+    r->n_tiles = t1 - t0;
+    r->codes = p->codes + 2 * (size_t)b0;
+    r->valid = p->valid + b0;
+    r->read_len = (uint32_t*)malloc(sizeof(uint32_t) * (n + 1));
+    r->read_blk = (uint32_t*)malloc(sizeof(uint32_t) * (n + 1));
+    r->tile_read = (uint32_t*)malloc(sizeof(uint32_t) * (r->n_tiles + 1));
+    r->tile_blk = (uint32_t*)malloc(sizeof(uint32_t) * (r->n_tiles + 1));
+    if (!r->read_len || !r->read_blk || !r->tile_read || !r->tile_blk) { free_reads(r); return lrb_set_error(LRB_ENOMEM, "out of memory (slice index)"); }
+    uint64_t bases = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        r->read_len[i] = p->read_len[read_lo + i];
+        r->read_blk[i] = p->read_blk[read_lo + i] - b0;
+        bases += r->read_len[i];
+    }
+    r->read_blk[n] = b1 - b0;
+    r->total_bases = bases;
+    for (uint64_t t = 0; t < r->n_tiles; ++t) {
+        r->tile_read[t] = p->tile_read[t0 + t] - (uint32_t)read_lo;
+        r->tile_blk[t] = p->tile_blk[t0 + t] - b0;
+    }
+    if (p->exc_ready) {  // the parent's exception list is ascending by block: the slice owns a contiguous stretch of it
+        const uint32_t* e0 = std::lower_bound(p->exc_blk, p->exc_blk + p->n_exc, b0);
+        const uint32_t* e1 = std::lower_bound(p->exc_blk, p->exc_blk + p->n_exc, b1);
+        const uint64_t ne = (uint64_t)(e1 - e0);
+        bool p1 = false, p2 = false;
+        r->exc_blk = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (ne + 1), &p1, false);
+        r->exc_valid = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (ne + 1), &p2, false);
+        if (!r->exc_blk || !r->exc_valid) { free_reads(r); return lrb_set_error(LRB_ENOMEM, "out of memory (slice exceptions)"); }
+        for (uint64_t i = 0; i < ne; ++i) {
+            r->exc_blk[i] = e0[i] - b0;
+            r->exc_valid[i] = p->exc_valid[(e0 - p->exc_blk) + i];
+        }
+        r->n_exc = ne;
+        r->exc_pinned = false;
+        r->exc_ready = true;
+    }
     *out = r;
     return LRB_OK;
 }

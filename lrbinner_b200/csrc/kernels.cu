@@ -11,6 +11,8 @@
 // No tensor cores anywhere: nothing here is a dense contraction (BASELINE.json north_star).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -281,12 +283,16 @@ k_profile_values(const uint32_t* __restrict__ counts, const uint32_t* __restrict
     out[idx] = (double)fixed6(counts[idx], den, !COMP) / 1e6;
 }
 
-thread_local bool t_luts_ready[64] = {false};
+// the LUTs are per device, not per thread (the multi-GPU host pipeline drives every device from a thread of its own)
+std::atomic<bool> g_luts_ready[64];
+std::mutex g_luts_mutex;
 
 int ensure_luts() {
     int dev = 0;
     LRB_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && t_luts_ready[dev]) return LRB_OK;
+    if (dev < 64 && g_luts_ready[dev].load(std::memory_order_acquire)) return LRB_OK;
+    std::lock_guard<std::mutex> lock(g_luts_mutex);
+    if (dev < 64 && g_luts_ready[dev].load(std::memory_order_acquire)) return LRB_OK;
     uint16_t l3[64], l4[256], l5[1024];
     lrb_kmer_lut(3, l3);
     lrb_kmer_lut(4, l4);
@@ -294,7 +300,7 @@ int ensure_luts() {
     LRB_CUDA(cudaMemcpyToSymbol(g_lut3, l3, sizeof l3));
     LRB_CUDA(cudaMemcpyToSymbol(g_lut4, l4, sizeof l4));
     LRB_CUDA(cudaMemcpyToSymbol(g_lut5, l5, sizeof l5));
-    if (dev < 64) t_luts_ready[dev] = true;
+    if (dev < 64) g_luts_ready[dev].store(true, std::memory_order_release);
     return LRB_OK;
 }
 
@@ -378,7 +384,7 @@ extern "C" int lrb_dev_add_planes(uint32_t* dst, uint64_t dst_pitch_words, const
         return lrb_set_error(LRB_EINVAL, "lrb_dev_add_planes: rows, pitches and pointers must be 16-byte aligned");
     if (!rows || !width_words || n_planes <= 0) return LRB_OK;
     const uint64_t total4 = (uint64_t)rows * (width_words / 4);
-    const unsigned grid = (unsigned)std::min<uint64_t>((total4 + 255) / 256, 148ull * 16);
+    const unsigned grid = (unsigned)std::min<uint64_t>((total4 + 255) / 256, (uint64_t)sm_count() * 16);
     k_add_planes<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), dst_pitch_words / 4, reinterpret_cast<const uint4*>(src),
                                                          plane_words / 4, n_planes, width_words / 4, total4);
     LRB_CUDA(cudaGetLastError());

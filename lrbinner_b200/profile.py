@@ -64,6 +64,14 @@ class PackedReads:
         check(lib.lrb_reads_from_lengths(_ptr(lengths), len(lengths), C.byref(h)))
         return cls(h)
 
+    def slice(self, read_lo, read_hi):
+        """Reads [read_lo, read_hi) as a read set of its own (shares the packed stream with self, which it keeps alive)."""
+        h = C.c_void_p()
+        check(lib.lrb_reads_slice(self._h, int(read_lo), int(read_hi), C.byref(h)))
+        s = PackedReads(h)
+        s._parent = self
+        return s
+
     # -- accessors ------------------------------------------------------------------------------
     n_reads = property(lambda self: int(self.view.n_reads))
     n_blocks = property(lambda self: int(self.view.n_blocks))
@@ -115,14 +123,20 @@ class PackedReads:
 
 
 class Context:
-    """One GPU.  profile() is the seam-to-seam call: host buffers in, host buffers out."""
+    """One GPU, or several driven from this process (device = an ordinal or a list of ordinals; the first is the
+    primary and ends up with the complete table).  profile() is the seam-to-seam call: host buffers in, host buffers out."""
 
     def __init__(self, device=0):
         self._h = C.c_void_p()
-        check(lib.lrb_ctx_create(int(device), C.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            check(lib.lrb_ctx_create_multi(ids, len(device), C.byref(self._h)))
+        else:
+            check(lib.lrb_ctx_create(int(device), C.byref(self._h)))
         self.device = device
 
-    def profile(self, reads, k=None, bin_size=None, bins=None, want_table=False, use_loaded_table=False, out=None):
+    def profile(self, reads, k=None, bin_size=None, bins=None, want_table=False, use_loaded_table=False, out=None,
+                keep_table=False):
         """Returns dict(comp=[N,P] u32, hist=[N,bins] u32, sums=[N] u32, table=[2^30] u32) for the requested parts.
         `out` may carry preallocated (ideally page-locked) arrays under the same keys."""
         n = reads.n_reads
@@ -147,8 +161,15 @@ class Context:
                                    int(bin_size) if bin_size is not None else 1, int(bins) if bins is not None else 1,
                                    _ptr(comp) if comp is not None else None, _ptr(hist) if hist is not None else None,
                                    _ptr(sums) if sums is not None else None, _ptr(table) if table is not None else None,
-                                   1 if use_loaded_table else 0))
+                                   (_lib.PROFILE_USE_LOADED_TABLE if use_loaded_table else 0) |
+                                   (_lib.PROFILE_KEEP_TABLE if keep_table else 0)))
         return {"comp": comp, "hist": hist, "sums": sums, "table": table}
+
+    def info(self):
+        """How the last profile() ran: devices, batches, table path, wall / exchange milliseconds."""
+        ri = _lib.RunInfo()
+        check(lib.lrb_ctx_last_info(self._h, C.byref(ri)))
+        return {f: getattr(ri, f) for f, _ in ri._fields_}
 
     def timings(self):
         ms = (C.c_float * 7)()

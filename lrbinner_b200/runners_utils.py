@@ -50,15 +50,17 @@ def run_15mer_vecs(reads_path, output, bin_size, bin_count, threads):
     check_proc(o, "Counting 15-mer profiles")
 
 
-def run_profile(reads_path, output, k_size, bin_size, bin_count, threads, write_table=True, write_npy=False):
+def run_profile(reads_path, output, k_size, bin_size, bin_count, threads, write_table=True, write_npy=False, n_gpus=0):
     """Fused stages 1_1 + 1_2 + 2_1: leaves com_profs, cov_profs (and 15mers-counts unless write_table=False,
-    needed by --resume with changed -bs/-bc) in {output}/profiles, byte-identical to the three separate calls."""
+    needed by --resume with changed -bs/-bc) in {output}/profiles, byte-identical to the three separate calls.
+    n_gpus > 1 shards the reads over that many GPUs of this node (0: LRB_GPUS from the environment, default 1);
+    the three separate runners above honour LRB_GPUS the same way.  Same files whatever the GPU count."""
     if not os.path.isdir(f"{output}/profiles"):
         os.makedirs(f"{output}/profiles")
 
     logger.debug(f"LIB::lrb_profile \"{reads_path}\" \"{output}\" {k_size} {bin_size} {bin_count} {threads}")
-    o = _lib.lib.lrb_profile(os.fsencode(reads_path), os.fsencode(output), int(k_size), int(bin_size), int(bin_count),
-                             int(threads), 1 if write_table else 0, 1 if write_npy else 0)
+    o = _lib.lib.lrb_profile_multi(os.fsencode(reads_path), os.fsencode(output), int(k_size), int(bin_size), int(bin_count),
+                                   int(threads), int(n_gpus), 1 if write_table else 0, 1 if write_npy else 0)
     check_proc(o, "Computing profiles")
 
 

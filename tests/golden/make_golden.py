@@ -141,6 +141,19 @@ def build_inputs():
             r = r[:p] + "N" + r[p + 1:]
         txt += f">read{i}\n{r}\n"
     files["g06_community.fa"] = txt
+    # contigs mode (pipelines.py:139-175): 15-mers are counted on the READS (g06_community.fa) while composition and
+    # coverage are computed for the FRAGMENTS of assembled contigs (runners_utils.py:53-75 split_contigs: contigs of
+    # >= 5000 bases are cut into 2500-base pieces plus the last 2500 bases once more).  Written with the extension
+    # .fasta so that it is not picked up as a self-contained golden input.
+    contigs = [genomes[0][100:3900], genomes[1][:5600], revcomp_str(genomes[1][200:5900]), genomes[2][500:2900], genomes[0][:1200].lower()]
+    frag = ""
+    i = 0
+    for n, c in enumerate(contigs):
+        subs = [c[x:x + 2500] for x in range(0, len(c), 2500)] + [c[-2500:]] if len(c) >= 5000 else [c]
+        for sc in subs:
+            frag += f">{n}_{i}\n{sc}\n"
+            i += 1
+    files["g10_fragments.fasta"] = frag
     return files
 
 
@@ -168,7 +181,9 @@ def main():
             f.write(txt)
     # a gzip copy of one input (gzopen path, io_utils.h:143)
     gz_write(os.path.join(HERE, "g09_community.fa.gz"), files["g06_community.fa"].encode())
-    inputs = sorted(list(files) + ["g09_community.fa.gz"])
+    inputs = sorted([f for f in files if not f.endswith(".fasta")] + ["g09_community.fa.gz"])
+    if "--contigs-only" in sys.argv:
+        inputs = []
     with tempfile.TemporaryDirectory(dir=os.environ.get("TMPDIR", "/tmp")) as tmp:
         for name in inputs:
             src = os.path.join(HERE, name)
@@ -188,6 +203,20 @@ def main():
                 gz_write(os.path.join(HERE, f"{stem}.cov_bs{bs}_bc{bc}.txt.gz"), open(out, "rb").read())
             os.remove(table)
             print(f"{name}: {len(keys)} non-zero table entries", flush=True)
+        # contigs mode: table of the reads, profiles of the fragments
+        table = os.path.join(tmp, "table")
+        frag = os.path.join(HERE, "g10_fragments.fasta")
+        oracle.ref_count_15mers(os.path.join(HERE, "g06_community.fa"), table, threads=2)
+        for k in (3, 4, 5):
+            out = os.path.join(tmp, "com")
+            oracle.ref_count_kmers(frag, out, k, threads=2)
+            gz_write(os.path.join(HERE, f"g10_contigs_mode.com_k{k}.txt.gz"), open(out, "rb").read())
+        for bs, bc in COV_PARAMS:
+            out = os.path.join(tmp, "cov")
+            oracle.ref_search_15mers(table, frag, out, bs, bc, threads=2)
+            gz_write(os.path.join(HERE, f"g10_contigs_mode.cov_bs{bs}_bc{bc}.txt.gz"), open(out, "rb").read())
+        os.remove(table)
+        print("g10_contigs_mode: reads g06_community.fa, fragments g10_fragments.fasta", flush=True)
 
 
 if __name__ == "__main__":

@@ -119,6 +119,142 @@ def test_dropin_three_stage_sequence_and_fused(tmp_path):
     assert np.array_equal(np.load(f"{out2}/profiles/cov_profs.npy"), want)
 
 
+def test_contigs_mode_seam_counts_on_reads_profiles_fragments(tmp_path):
+    """Contigs mode (pipelines.py:139-175): stage 2_4 counts the 15-mers of the READS, stages 3_1 / 4_1 run count-kmers and
+    search-15mers on {output}/fragments/contigs.fasta against that table.  Golden bytes: the reference tools run the same
+    way by tests/golden/make_golden.py (reads g06_community.fa, fragments g10_fragments.fasta)."""
+    reads = os.path.join(GOLDEN, "g06_community.fa")
+    frags = os.path.join(GOLDEN, "g10_fragments.fasta")
+    out = str(tmp_path)
+    runners_utils.run_15mer_counts(reads, out, 4)                       # stage 2_4
+    for k in (3, 4, 5):
+        runners_utils.run_kmers(frags, out, k, 4)                       # stage 3_1
+        assert open(f"{out}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, f"g10_contigs_mode.com_k{k}.txt.gz")), k
+    for bs, bc in COV_PARAMS:
+        runners_utils.run_15mer_vecs(frags, out, bs, bc, 4)             # stage 4_1
+        assert open(f"{out}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, f"g10_contigs_mode.cov_bs{bs}_bc{bc}.txt.gz")), (bs, bc)
+    # the same through one context: table of the reads kept in HBM, fragments searched against it
+    c = Context(0)
+    c.profile(PackedReads.from_file(reads, threads=2), keep_table=True)
+    fr = PackedReads.from_file(frags, threads=2)
+    r = c.profile(fr, bin_size=10, bins=8, use_loaded_table=True)
+    path = f"{out}/cov2"
+    assert _lib.lib.lrb_write_coverage_txt(path.encode(), _ptr(r["hist"]), _ptr(r["sums"]), fr.n_reads, 8, 2) == 0
+    assert open(path, "rb").read() == _gz(os.path.join(GOLDEN, "g10_contigs_mode.cov_bs10_bc8.txt.gz"))
+    c.close()
+    os.remove(f"{out}/profiles/15mers-counts")
+
+
+def _env(**kw):
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kw}
+        os.environ.update({k: str(v) for k, v in kw.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+@pytest.mark.parametrize("batch_bases", [4000, 20000])
+def test_streamed_batches_equal_the_resident_run(tmp_path, batch_bases):
+    """Bounded device memory (count-15mers.cpp:75-99 streams reads through a bounded queue): when the working set does not
+    fit, lrb_profile_host runs in batches — table accumulated over the batches, every batch shipped again for the search.
+    LRB_BATCH_BASES forces that on a small input; the files must be the reference tools' bytes all the same."""
+    src = os.path.join(GOLDEN, "g06_community.fa")
+    out = str(tmp_path)
+    with _env(LRB_BATCH_BASES=batch_bases):
+        runners_utils.run_profile(src, out, 4, 10, 8, 4, write_table=False)
+        assert open(f"{out}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.com_k4.txt.gz"))
+        assert open(f"{out}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.cov_bs10_bc8.txt.gz"))
+        # buffer level: synthetic reads with N / lowercase / edge lengths against the oracle, table included
+        spec = SynthSpec(1500, seed=8, n_rate=2e-3, lowercase_frac=0.03, edge_lengths=True, scale=0.004)
+        seqs = spec.host_sequences()
+        pr = spec.host_packed(threads=4)
+        c = Context(0)
+        res = c.profile(pr, k=3, bin_size=2, bins=6, want_table=True)
+        info = c.info()
+        assert info["n_batches"] > 1 and info["n_devices"] == 1 and info["lists_reused"] == 0
+        for path in ("direct",):
+            with _env(LRB_TABLE_PATH=path):
+                res_d = c.profile(pr, k=3, bin_size=2, bins=6, want_table=True)
+                assert c.info()["table_path"] == 0 and c.info()["n_batches"] > 1
+            for kk in ("comp", "hist", "sums", "table"):
+                assert np.array_equal(res[kk], res_d[kk]), kk
+        c.close()
+    comp, table, cov = _oracle_profile(seqs, [3], [(2, 6)])
+    _assert_table_equal(res["table"], table.array)
+    assert np.array_equal(res["comp"], comp[3])
+    assert np.array_equal(res["hist"], cov[(2, 6)][0]) and np.array_equal(res["sums"], cov[(2, 6)][1])
+    table.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("n_gpus", [2, 3, 4, 8])
+def test_multi_gpu_context_leaves_the_same_bytes(tmp_path, n_gpus):
+    """N GPUs through the boundary (lrb_ctx_create_multi / run_profile(n_gpus=)): reads sharded over the devices, private
+    tables summed over peer memory, every device searches its own reads.  Row i must still be read i
+    (search-15mers.cpp:26-48) and the files the reference tools' bytes — resident and streamed, 2 consecutive calls."""
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"{n_gpus} GPUs not available")
+    import hashlib
+    src = os.path.join(GOLDEN, "g06_community.fa")
+    with _env(LRB_MIN_BLOCKS_PER_DEVICE=1):
+        for rep, extra in enumerate(({}, {"LRB_BATCH_BASES": 9000}, {"LRB_XCHG_COPY3D": 1})):
+            out = str(tmp_path / f"o{rep}")
+            with _env(**extra):
+                runners_utils.run_profile(src, out, 3, 32, 10, 4, write_table=(rep == 0 and n_gpus == 2), n_gpus=n_gpus)
+            assert open(f"{out}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.com_k3.txt.gz"))
+            assert open(f"{out}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g06_community.cov_bs32_bc10.txt.gz"))
+            if rep == 0 and n_gpus == 2:
+                gold = np.load(os.path.join(GOLDEN, "g06_community.table.npz"))
+                h = hashlib.sha256()
+                with open(f"{out}/profiles/15mers-counts", "rb") as f:
+                    for blk in iter(lambda: f.read(1 << 24), b""):
+                        h.update(blk)
+                assert h.hexdigest() == str(gold["sha256"])
+                os.remove(f"{out}/profiles/15mers-counts")
+        # the three separate runners with LRB_GPUS (contigs mode: table of the reads, fragments searched on N GPUs)
+        out = str(tmp_path / "sep")
+        with _env(LRB_GPUS=n_gpus):
+            runners_utils.run_15mer_counts(src, out, 4)
+            frags = os.path.join(GOLDEN, "g10_fragments.fasta")
+            runners_utils.run_kmers(frags, out, 5, 4)
+            runners_utils.run_15mer_vecs(frags, out, 1, 5, 4)
+        assert open(f"{out}/profiles/com_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g10_contigs_mode.com_k5.txt.gz"))
+        assert open(f"{out}/profiles/cov_profs", "rb").read() == _gz(os.path.join(GOLDEN, "g10_contigs_mode.cov_bs1_bc5.txt.gz"))
+        os.remove(f"{out}/profiles/15mers-counts")
+    # a 20k-read synthetic set (both tables well filled, every bin hit) against the single-GPU run and the oracle's rows
+    spec = SynthSpec(20000, seed=77, n_rate=1e-4, lowercase_frac=0.001, edge_lengths=True, scale=0.02)
+    pr = spec.host_packed(threads=8)
+    one, many = Context(0), Context(list(range(n_gpus)))
+    a = one.profile(pr, k=4, bin_size=8, bins=12, want_table=True)
+    for step in range(2):        # twice: the second call re-zeroes tables the peers pulled from in the first
+        b = many.profile(pr, k=4, bin_size=8, bins=12, want_table=True)
+        info = many.info()
+        assert info["n_devices"] == n_gpus and info["n_batches"] == n_gpus and info["lists_reused"] == 1
+        for kk in ("comp", "hist", "sums", "table"):
+            assert np.array_equal(a[kk], b[kk]), (kk, step)
+    seqs = spec.host_sequences()
+    table = oracle.Table()
+    for s in seqs:
+        table.count(s)
+    for i in list(range(0, 20000, 397)) + [19999]:
+        hraw, hsum, _ = table.coverage(seqs[i], 8, 12)
+        assert np.array_equal(b["hist"][i], hraw.astype(np.uint32)) and b["sums"][i] == hsum, i
+        assert np.array_equal(b["comp"][i], oracle.composition(seqs[i], 4)[0].astype(np.uint32)), i
+    table.close()
+    one.close()
+    many.close()
+
+
 def test_missing_input_gives_empty_outputs_like_the_tools(tmp_path):
     out = str(tmp_path)
     runners_utils.run_kmers(str(tmp_path / "nope.fa"), out, 3, 2)

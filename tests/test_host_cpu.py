@@ -198,6 +198,39 @@ def test_from_sequences_and_lengths_layout():
     assert np.array_equal(pl.tile_read, pr.tile_read) and not pl.codes.any()
 
 
+def test_reads_slice_is_a_read_set_of_its_own():
+    """lrb_reads_slice (device shards / batches of the host pipeline): same reads, indices rebased, exceptions kept."""
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i in range(300):
+        n = int(rng.choice([0, 1, 14, 15, 31, 32, 33, 500, 9000]))
+        s = bytearray(rng.choice(list(b"ACGT"), n).astype(np.uint8).tobytes())
+        if n > 40 and i % 7 == 0:
+            s[n // 2] = ord("N")
+        if n > 40 and i % 11 == 0:
+            s = bytearray(bytes(s).lower())
+        seqs.append(bytes(s))
+    pr = PackedReads.from_sequences(seqs, threads=3)
+    for lo, hi in [(0, 300), (0, 1), (17, 18), (5, 120), (120, 300), (299, 300), (40, 40)]:
+        sl = pr.slice(lo, hi)
+        assert sl.n_reads == hi - lo and sl.total_bases == sum(len(s) for s in seqs[lo:hi])
+        assert sl.n_blocks == sum(len(s) // 32 + 1 for s in seqs[lo:hi])
+        _check_packing(sl, seqs[lo:hi])
+        # the slice's exception list rebuilds its validity words exactly
+        blk, word = sl.exceptions()
+        want = _default_valid(sl)[:sl.n_blocks]
+        if len(blk):
+            want[blk] = word
+        assert np.array_equal(want, sl.valid[:sl.n_blocks])
+        # tiles: <= 256 blocks of one read each, covering every block once, in order
+        covered = 0
+        for t in range(sl.n_tiles):
+            r, b = int(sl.tile_read[t]), int(sl.tile_blk[t])
+            assert b == covered and int(sl.read_blk[r]) <= b < int(sl.read_blk[r + 1])
+            covered = min(b + 256, int(sl.read_blk[r + 1]))
+        assert covered == sl.n_blocks
+
+
 def _default_valid(pr):
     blk, ln = np.array(pr.read_blk, dtype=np.int64), np.array(pr.read_len, dtype=np.int64)
     want = np.zeros(pr.n_blocks + 1, dtype=np.uint32)
