@@ -279,6 +279,15 @@ void lrb_pinned_free(void* p);
 int lrb_ctx_table_load(lrb_ctx* ctx, const char* path);          /* readKmerFile -> HBM */
 int lrb_ctx_table_save(lrb_ctx* ctx, const char* path);          /* HBM -> writeKmerFile format */
 
+/* Launch accounting (csrc/prof.cu).  lrb_prof_launches: kernels this library has launched since it was loaded (always
+ * counted; bench.py's gpu_launches).  lrb_prof_enable(1) additionally brackets every launch with CUDA events on the stream
+ * it is launched on (and forgets earlier records); after synchronising, lrb_prof_report writes one line per kernel,
+ * "name launches total_ms".  This is how bench.py quotes single-kernel durations inside its timed region without a
+ * profiler attached.  Returns the previous state. */
+uint64_t lrb_prof_launches(void);
+int lrb_prof_enable(int on);
+int lrb_prof_report(char* buf, size_t cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Host text / file epilogue (multi-threaded, exact "%f").
  * ---------------------------------------------------------------------------------------------- */

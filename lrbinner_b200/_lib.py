@@ -109,6 +109,9 @@ _SIG = {
     "lrb_pinned_free": (None, [_P]),
     "lrb_ctx_table_load": (C.c_int, [_P, C.c_char_p]),
     "lrb_ctx_table_save": (C.c_int, [_P, C.c_char_p]),
+    "lrb_prof_launches": (C.c_uint64, []),
+    "lrb_prof_enable": (C.c_int, [C.c_int]),
+    "lrb_prof_report": (C.c_int, [_P, C.c_size_t]),
     "lrb_fixed6": (C.c_uint32, [C.c_uint32, C.c_uint32, C.c_int]),
     "lrb_write_composition_txt": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.c_int, C.c_int]),
     "lrb_write_coverage_txt": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, C.c_int, C.c_int]),
@@ -130,6 +133,17 @@ for _name, (_res, _args) in _SIG.items():
     _fn = getattr(lib, _name)   # AttributeError here == the .so does not export a declared symbol
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+def prof_report():
+    """{kernel: (launches, total_ms)} recorded since lrb_prof_enable(1); synchronise the device(s) first."""
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.lrb_prof_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split()
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def last_error():

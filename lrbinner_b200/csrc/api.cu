@@ -969,7 +969,7 @@ extern "C" int lrb_dev_synth(const lrb_reads_view* dev, const lrb_synth_params* 
     if (!dev || !p || !glen || !meta || p->n_genomes == 0) return lrb_set_error(LRB_EINVAL, "lrb_dev_synth: bad argument");
     if (dev->n_reads == 0) return LRB_OK;
     const unsigned grid = (unsigned)((dev->n_reads + 127) / 128);
-    k_synth<<<grid, 128, 0, (cudaStream_t)stream>>>(*dev, *p, glen, meta, const_cast<uint32_t*>(dev->codes), const_cast<uint32_t*>(dev->valid));
+    LRB_LAUNCH("k_synth", (cudaStream_t)stream, k_synth<<<grid, 128, 0, (cudaStream_t)stream>>>(*dev, *p, glen, meta, const_cast<uint32_t*>(dev->codes), const_cast<uint32_t*>(dev->valid)));
     CTX_CUDA(cudaGetLastError());
     return LRB_OK;
 }

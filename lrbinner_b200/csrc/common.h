@@ -17,6 +17,24 @@ int lrb_set_error(int code, const char* fmt, ...);
     } while (0)
 #endif
 
+// One kernel launch: always counted, timed with CUDA events on its own stream when lrb_prof_enable(1) (csrc/prof.cu).
+class ProfScope {
+public:
+    ProfScope(const char* name, void* stream);
+    ~ProfScope();
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
+private:
+    const char* name_;
+    void* stream_;
+    void* a_;
+};
+#define LRB_LAUNCH(name, stream, ...)            \
+    do {                                         \
+        ProfScope lrb_ps_(name, (void*)(stream)); \
+        __VA_ARGS__;                             \
+    } while (0)
+
 // host-side internals shared between ingest.cpp / format.cpp / api.cu
 struct lrb_reads {
     uint64_t n_reads = 0, n_blocks = 0, n_tiles = 0, total_bases = 0;

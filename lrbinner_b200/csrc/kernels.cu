@@ -329,9 +329,9 @@ extern "C" int lrb_dev_composition(const lrb_reads_view* dev, int k, uint32_t* c
     const uint64_t ntile = tile_hi - tile_lo;
     const unsigned grid = (unsigned)((ntile + kWarpsPerCta - 1) / kWarpsPerCta);
     cudaStream_t st = (cudaStream_t)stream;
-    if (k == 3) k_composition<3><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi);
-    else if (k == 4) k_composition<4><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi);
-    else k_composition<5><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi);
+    if (k == 3) LRB_LAUNCH("k_composition", st, k_composition<3><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi));
+    else if (k == 4) LRB_LAUNCH("k_composition", st, k_composition<4><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi));
+    else LRB_LAUNCH("k_composition", st, k_composition<5><<<grid, kCtaThreads, 0, st>>>(*dev, counts, tile_lo, tile_hi));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -348,15 +348,15 @@ extern "C" int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     cudaStream_t st = (cudaStream_t)stream;
     const bool filter = !(key_lo == 0 && key_hi >= kTableEntries);
-    if (filter) k_count15<true><<<grid, threads, 0, st>>>(dev->codes, dev->valid, table, blk_lo, blk_hi, key_lo, key_hi);
-    else k_count15<false><<<grid, threads, 0, st>>>(dev->codes, dev->valid, table, blk_lo, blk_hi, key_lo, key_hi);
+    if (filter) LRB_LAUNCH("k_count15", st, k_count15<true><<<grid, threads, 0, st>>>(dev->codes, dev->valid, table, blk_lo, blk_hi, key_lo, key_hi));
+    else LRB_LAUNCH("k_count15", st, k_count15<false><<<grid, threads, 0, st>>>(dev->codes, dev->valid, table, blk_lo, blk_hi, key_lo, key_hi));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
 
 extern "C" int lrb_dev_mirror(uint32_t* table, void* stream) {
     if (!table) return lrb_set_error(LRB_EINVAL, "lrb_dev_mirror: null table");
-    k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table);
+    LRB_LAUNCH("k_mirror", (cudaStream_t)stream, k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -385,8 +385,8 @@ extern "C" int lrb_dev_add_planes(uint32_t* dst, uint64_t dst_pitch_words, const
     if (!rows || !width_words || n_planes <= 0) return LRB_OK;
     const uint64_t total4 = (uint64_t)rows * (width_words / 4);
     const unsigned grid = (unsigned)std::min<uint64_t>((total4 + 255) / 256, (uint64_t)sm_count() * 16);
-    k_add_planes<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), dst_pitch_words / 4, reinterpret_cast<const uint4*>(src),
-                                                         plane_words / 4, n_planes, width_words / 4, total4);
+    LRB_LAUNCH("k_add_planes", (cudaStream_t)stream, k_add_planes<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4*>(dst), dst_pitch_words / 4, reinterpret_cast<const uint4*>(src),
+                                                         plane_words / 4, n_planes, width_words / 4, total4));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -407,11 +407,11 @@ extern "C" int lrb_dev_fill_valid(const lrb_reads_view* dev, const uint32_t* exc
     uint32_t* valid = const_cast<uint32_t*>(dev->valid);
     if (dev->n_reads) {
         const uint64_t threads = dev->n_reads * 32;
-        k_default_valid<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(*dev, valid);
+        LRB_LAUNCH("k_default_valid", st, k_default_valid<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(*dev, valid));
     } else {
         LRB_CUDA(cudaMemsetAsync(valid, 0, sizeof(uint32_t) * (dev->n_blocks + 1), st));
     }
-    if (n_exc) k_patch_valid<<<(unsigned)((n_exc + 255) / 256), 256, 0, st>>>(exc_blk, exc_valid, n_exc, valid);
+    if (n_exc) LRB_LAUNCH("k_patch_valid", st, k_patch_valid<<<(unsigned)((n_exc + 255) / 256), 256, 0, st>>>(exc_blk, exc_valid, n_exc, valid));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -436,9 +436,9 @@ extern "C" int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, 
         LRB_CUDA(cudaFuncSetAttribute(k_search15<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (filter)
-        k_search15<true><<<grid, kCtaThreads, smem, st>>>(*dev, table, S32, magic, (uint32_t)bins, hist, sums, tile_lo, tile_hi, key_lo, key_hi);
+        LRB_LAUNCH("k_search15", st, k_search15<true><<<grid, kCtaThreads, smem, st>>>(*dev, table, S32, magic, (uint32_t)bins, hist, sums, tile_lo, tile_hi, key_lo, key_hi));
     else
-        k_search15<false><<<grid, kCtaThreads, smem, st>>>(*dev, table, S32, magic, (uint32_t)bins, hist, sums, tile_lo, tile_hi, key_lo, key_hi);
+        LRB_LAUNCH("k_search15", st, k_search15<false><<<grid, kCtaThreads, smem, st>>>(*dev, table, S32, magic, (uint32_t)bins, hist, sums, tile_lo, tile_hi, key_lo, key_hi));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -448,8 +448,8 @@ extern "C" int lrb_dev_pack_ascii(const lrb_reads_view* dev, const char* bases, 
     if (dev->n_reads == 0) return LRB_OK;
     const uint64_t threads = dev->n_reads * 32;
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    k_pack_ascii<<<grid, 256, 0, (cudaStream_t)stream>>>(*dev, bases, offsets, const_cast<uint32_t*>(dev->codes),
-                                                        const_cast<uint32_t*>(dev->valid));
+    LRB_LAUNCH("k_pack_ascii", (cudaStream_t)stream, k_pack_ascii<<<grid, 256, 0, (cudaStream_t)stream>>>(*dev, bases, offsets, const_cast<uint32_t*>(dev->codes),
+                                                        const_cast<uint32_t*>(dev->valid)));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -460,7 +460,7 @@ extern "C" int lrb_dev_format_composition(const uint32_t* counts, const uint32_t
     if (!P || !text || (n_reads && (!counts || !read_len))) return lrb_set_error(LRB_EINVAL, "lrb_dev_format_composition: bad argument");
     if (!n_reads) return LRB_OK;
     const uint64_t total = n_reads * (uint64_t)P;
-    k_format_rows<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, read_len, n_reads, (uint32_t)P, k, text);
+    LRB_LAUNCH("k_format_rows", (cudaStream_t)stream, k_format_rows<true><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(counts, read_len, n_reads, (uint32_t)P, k, text));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -473,8 +473,8 @@ extern "C" int lrb_dev_profile_values(const uint32_t* counts, const uint32_t* de
     if (!n_reads) return LRB_OK;
     const uint64_t total = n_reads * (uint64_t)width;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (k) k_profile_values<true><<<grid, 256, 0, (cudaStream_t)stream>>>(counts, denom, n_reads, (uint32_t)width, k, out);
-    else k_profile_values<false><<<grid, 256, 0, (cudaStream_t)stream>>>(counts, denom, n_reads, (uint32_t)width, 0, out);
+    if (k) LRB_LAUNCH("k_profile_values", (cudaStream_t)stream, k_profile_values<true><<<grid, 256, 0, (cudaStream_t)stream>>>(counts, denom, n_reads, (uint32_t)width, k, out));
+    else LRB_LAUNCH("k_profile_values", (cudaStream_t)stream, k_profile_values<false><<<grid, 256, 0, (cudaStream_t)stream>>>(counts, denom, n_reads, (uint32_t)width, 0, out));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -484,7 +484,7 @@ extern "C" int lrb_dev_format_coverage(const uint32_t* hist, const uint32_t* sum
     if (bins <= 0 || !text || (n_reads && (!hist || !sums))) return lrb_set_error(LRB_EINVAL, "lrb_dev_format_coverage: bad argument");
     if (!n_reads) return LRB_OK;
     const uint64_t total = n_reads * (uint64_t)bins;
-    k_format_rows<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hist, sums, n_reads, (uint32_t)bins, 0, text);
+    LRB_LAUNCH("k_format_rows", (cudaStream_t)stream, k_format_rows<false><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(hist, sums, n_reads, (uint32_t)bins, 0, text));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

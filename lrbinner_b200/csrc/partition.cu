@@ -809,7 +809,7 @@ extern "C" int lrb_dev_fill_blk_read(const lrb_reads_view* dev, uint32_t* blk_re
     if (!dev || !blk_read) return lrb_set_error(LRB_EINVAL, "lrb_dev_fill_blk_read: null argument");
     if (!dev->n_reads) return LRB_OK;
     const uint64_t threads = dev->n_reads * 32;
-    k_fill_blk_read<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*dev, blk_read);
+    LRB_LAUNCH("k_fill_blk_read", (cudaStream_t)stream, k_fill_blk_read<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*dev, blk_read));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }
@@ -884,14 +884,14 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
     const bool full = part->key_lo == 0 && part->key_hi >= kTableEntries;
     const uint32_t* br = part->has_rids ? blk_read : nullptr;
     if (full)
-        k_step_hist<true><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T);
+        LRB_LAUNCH("k_step_hist", st, k_step_hist<true><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T));
     else
-        k_step_hist<false><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T);
-    k_group_scan<<<nb, 256, 0, st>>>(T, n_groups, meta, c);
-    k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity);
+        LRB_LAUNCH("k_step_hist", st, k_step_hist<false><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T));
+    LRB_LAUNCH("k_group_scan", st, k_group_scan<<<nb, 256, 0, st>>>(T, n_groups, meta, c));
+    LRB_LAUNCH("k_chunk_scan", st, k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity));
 #define LRB_LAUNCH_PART(RID, FULLK)                                                                                                   \
-    k_partition<RID, FULLK><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, \
-                                                               shift, nb, n_steps, G, step0, T, meta, c, part->keys)
+    LRB_LAUNCH("k_partition", st, k_partition<RID, FULLK><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, \
+                                                               shift, nb, n_steps, G, step0, T, meta, c, part->keys))
     if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
     else { if (full) LRB_LAUNCH_PART(false, true); else LRB_LAUNCH_PART(false, false); }
 #undef LRB_LAUNCH_PART
@@ -904,10 +904,10 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
     case LG:                                                                                                            \
         if (strided) {                                                                                                  \
             LRB_CUDA(cudaFuncSetAttribute(k2_partition<LG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2)); \
-            k2_partition<LG, true><<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y);            \
+            LRB_LAUNCH("k2_partition", st, k2_partition<LG, true><<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y));            \
         } else {                                                                                                        \
             LRB_CUDA(cudaFuncSetAttribute(k2_partition<LG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemL2)); \
-            k2_partition<LG, false><<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y);           \
+            LRB_LAUNCH("k2_partition", st, k2_partition<LG, false><<<Y.n_cta, kL2Threads, kSmemL2, st>>>(part->keys, meta, c, part->sub, Y));           \
         }                                                                                                               \
         break
         const bool strided = Y.strided != 0;
@@ -1014,16 +1014,16 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     if (count_batched) {  // count only: every bucket in one launch each of the two kernels (the second only counts flagged buckets)
         const uint32_t base0 = part->key_lo + ((uint32_t)bucket_lo << shift);
         const dim3 g1(Y.nsub, (unsigned)(bucket_hi - bucket_lo)), g2(grid, (unsigned)(bucket_hi - bucket_lo));
-        k_count_smem<<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table);
-        k_count_keys<<<g2, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, base0, shift, hi_mask2, table, 1);
+        LRB_LAUNCH("k_count_smem", st, k_count_smem<<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table));
+        LRB_LAUNCH("k_count_keys", st, k_count_keys<<<g2, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, base0, shift, hi_mask2, table, 1));
     }
     const bool search_batched = do_search && !do_count && bucket_hi > bucket_lo;
     if (search_batched) {
         const uint32_t base0 = part->key_lo + ((uint32_t)bucket_lo << shift);
         const dim3 gs(sgrid, (unsigned)(bucket_hi - bucket_lo));
 #define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
-    k_search_keys<LUT, UN><<<gs, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, L, T, base0, hi_mask2, shift, table, S32, magic, \
-                                               (uint32_t)bins, hist)
+    LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN><<<gs, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, L, T, base0, hi_mask2, shift, table, S32, magic, \
+                                               (uint32_t)bins, hist))
         if (use_lut) LRB_LAUNCH_SEARCH(true, 4);
         else if (unroll8) LRB_LAUNCH_SEARCH(false, 8);
         else LRB_LAUNCH_SEARCH(false, 4);
@@ -1031,12 +1031,12 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     }
     for (int b = bucket_lo; b < bucket_hi && !count_batched && !search_batched; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
-        if (smem_count) k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table);
-        if (do_count) k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, shift, hi_mask2, table, smem_count ? 1 : 0);
+        if (smem_count) LRB_LAUNCH("k_count_smem", st, k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table));
+        if (do_count) LRB_LAUNCH("k_count_keys", st, k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, shift, hi_mask2, table, smem_count ? 1 : 0));
         if (do_search) {
 #define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
-    k_search_keys<LUT, UN><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \
-                                                  (uint32_t)bins, hist)
+    LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \
+                                                  (uint32_t)bins, hist))
             if (use_lut) LRB_LAUNCH_SEARCH(true, 4);
             else if (unroll8) LRB_LAUNCH_SEARCH(false, 8);
             else LRB_LAUNCH_SEARCH(false, 4);
@@ -1044,7 +1044,7 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
         }
     }
     if (do_search && part->n_reads && bucket_hi == part->n_buckets)
-        k_row_sums<<<(unsigned)((part->n_reads + 255) / 256), 256, 0, st>>>(hist, sums, part->n_reads, (uint32_t)bins);
+        LRB_LAUNCH("k_row_sums", st, k_row_sums<<<(unsigned)((part->n_reads + 255) / 256), 256, 0, st>>>(hist, sums, part->n_reads, (uint32_t)bins));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

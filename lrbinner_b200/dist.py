@@ -133,6 +133,18 @@ class CudaEngine:
             print("[feed timeline ms] " + " ".join(f"{nm}={tl[0][1].elapsed_time(e):.1f}" for nm, e in tl) +
                   f" chunks={[(a, b, self._blocks(a, b)) for a, b in chunks][:3]}", file=sys.stderr, flush=True)
 
+    def verify(self):
+        """Synchronises and raises LrbError(LRB_ENOMEM) if the last partition did not fit the workspace (the lists are
+        then incomplete and every apply was a no-op).  Later steps over a rectangle already seen skip the synchronising
+        check so that steps stay asynchronous; a driver that re-uploads DIFFERENT reads into the same DeviceReads calls
+        reset() first (or verify() at its next synchronisation point)."""
+        return self.ws.check()
+
+    def reset(self):
+        """Forget which rectangles were verified (the reads behind the DeviceReads changed)."""
+        self._verified.clear()
+        self._rect = None
+
     def mirror(self, table):
         self.p.dev_mirror(table)
 
@@ -468,206 +480,3 @@ class _EventTimers:
         for (_, a), (name, b) in zip(self.ev[:-1], self.ev[1:]):
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
-
-
-def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_peak, peak_src, metric, bs, bc):
-    """N > 1 leg of bench.py: weak scaling — the global read set is `world` shards of the config's size drawn
-    from ONE community (one global 15-mer table).  Times every plan once, keeps the fastest for the K steps."""
-    import torch
-    import torch.distributed as dist
-    from .profile import COMP_WIDTH, DeviceReads, dev_fill_valid
-    from .synth import SynthSpec
-
-    k = cfg["k"]
-    n_shard = args.reads or cfg["n_reads"]
-    # every rank materialises the whole global set in HBM (plans A/B scan all reads; plan X touches only its own)
-    spec = SynthSpec(n_shard * world, lengths=cfg["lengths"], errors=cfg["errors"], seed=cfg["seed"])
-    dr, layout = spec.device_reads(dev)
-    n, L = spec.n_reads, spec.total_bases
-    eng = CudaEngine(dr, workspace_entries=int(L / world * 1.25) + (1 << 20))
-    table = torch.zeros(TABLE_ENTRIES, dtype=torch.int32, device=dev)
-    xg = exchange_group(world)
-    px = None
-    try:                                                  # copy-engine exchange over peer memory (needs symmetric memory on this node)
-        px = PeerExchange(dev)
-    except Exception as ex:
-        if rank == 0:
-            print(f"[lrb] peer-memory exchange unavailable ({ex!r}); NCCL exchange only", file=__import__("sys").stderr)
-    ok = torch.tensor([1 if px is not None else 0], device=dev)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if not int(ok.item()):
-        px = None
-    if px is not None:
-        del table
-        table = px.table                                  # one 4 GiB table per rank, in symmetric memory (all plans use it)
-
-    def timed(plan, steps):
-        dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        tm = None
-        for _ in range(steps):
-            tm = _EventTimers(torch)
-            res = profile_distributed(eng, k, bs, bc, plan.split("/")[0], table=table, timers=tm, pipeline_exchange=not plan.endswith("/unpipelined"),
-                                      xgroup=xg, peer_exchange=px if plan.endswith("/p2p") else None)
-        b.record()
-        dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b) / steps], device=dev)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), res, tm.phases_ms()
-
-    plan_ms, checks = {}, {}
-    for plan in PLANS + ("readshard_ar/unpipelined",) + (("readshard_ar/p2p",) if px is not None else ()):
-        timed(plan, 1)                                   # warm-up (NCCL channels, allocator)
-        plan_ms[plan], res, _ = timed(plan, max(1, args.warmup - 1))
-        tot = torch.stack([res["sums"].to(torch.int64).sum(), res["hist"].to(torch.int64).sum(), res["comp"].to(torch.int64).sum()])
-        dist.all_reduce(tot)
-        checks[plan] = [int(x) for x in tot.tolist()]
-    assert len({tuple(v) for v in checks.values()}) == 1, f"plans disagree: {checks}"
-    valid_windows = checks[PLANS[0]][0]
-    assert checks[PLANS[0]][1] == valid_windows
-    best = min(plan_ms, key=plan_ms.get)
-    sampler = ClockSampler(dev.index)
-    sampler.start()
-    ms_step, res, phases = timed(best, args.steps)
-    clocks = sampler.stop()
-    nbk = eng.ws.part.n_buckets
-    # composition + 4 partition kernels (step hist, two scans, partition) + per-bucket count and search kernels + row sums
-    # (+ mirror; plan B partitions twice)
-    # our kernels per step: composition + per chunk (step_hist, group_scan, chunk_scan, partition, k2_partition) + count
-    # (k_count_smem, k_count_keys: one launch each over all buckets) + search launches + k_row_sums + mirror
-    # (+ lrb_dev_add_planes per round of the peer exchange; plan B partitions twice)
-    nch = max(1, eng.ws.part.n_chunks)
-    base = 1 + 5 * nch + 2 + 1 + 1
-    launches = {"keyshard_rs": base + 1, "keyshard_ag": base + 4 * nch + 1, "readshard_ar": base + nbk // 2,
-                "readshard_ar/unpipelined": base + 1, "readshard_ar/p2p": base + 2 * 8}[best] * args.steps
-
-    # e2e: every step also moves this rank's inputs host->device and its result rows device->host
-    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    dr.download_into(layout)
-    h_codes = torch.from_numpy(layout.codes.view(np.int32))   # whole global set; page-locked only if the host allowed that much
-    # validity crosses PCIe as the exception list only (0 entries for pure-ACGT reads); the bitmap is rebuilt on the device
-    layout.index_valid(threads=os.cpu_count() or 8)
-    exc_blk, exc_word = layout.exceptions()
-    h_exc = [pin(torch.from_numpy(a.view(np.int32))).copy_(torch.from_numpy(a.view(np.int32))) for a in (exc_blk, exc_word)]
-    d_exc = [torch.empty(len(exc_blk), dtype=torch.int32, device=dev) for _ in range(2)]
-    if best.startswith("readshard_ar"):   # only the own shard's blocks are needed on this rank
-        lo, hi = own_range(n, world, rank)
-        rb = layout.read_blk
-        b0, b1 = int(rb[lo]), int(rb[hi])
-    else:
-        b0, b1 = 0, layout.n_blocks
-    if best.startswith("readshard_ar") and world > 1:
-        # this rank ships only its own shard: give that a page-locked buffer of its own (8 ranks x the global set would
-        # ask the host for more pinned memory than it grants, and the copies would silently go through pageable staging)
-        own = pin(h_codes[2 * b0:2 * b1])
-        own.copy_(h_codes[2 * b0:2 * b1])
-        h_own, own_w0 = own, 2 * b0
-    else:
-        h_own, own_w0 = h_codes, 0
-    out_h = {kk: pin(res[kk]) for kk in ("comp", "hist", "sums")}
-
-    # chunk plan of this rank's blocks (cut at read boundaries) for the pipelined plan-X step
-    rb = np.asarray(layout.read_blk)
-    if best.startswith("readshard_ar"):
-        n_ch = 16
-        cr = [lo] + [max(lo, min(hi, int(np.searchsorted(rb, b0 + (b1 - b0) * j // n_ch, side="right")) - 1)) for j in range(1, n_ch)] + [hi]
-        cr = sorted(set(cr))
-    else:
-        cr = None
-    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    marks = {}
-
-    def e2e_step():
-        main = torch.cuda.current_stream()
-        if cr is None or len(cr) < 2:          # key-sharded plans need every read on every rank before anything starts
-            dr.codes[2 * b0:2 * b1].copy_(h_codes[2 * b0:2 * b1], non_blocking=True)
-            for d, h in zip(d_exc, h_exc):
-                d.copy_(h, non_blocking=True)
-            dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
-            r = profile_distributed(eng, k, bs, bc, best.split("/")[0], table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg,
-                                    peer_exchange=px if best.endswith("/p2p") else None)
-            for kk in out_h:
-                out_h[kk].copy_(r[kk], non_blocking=True)
-            return
-        # plan X: H2D in chunks on a copy stream; composition + key partition of chunk j run while chunk j+1 is on PCIe;
-        # the composition rows go home on a second copy stream while the table passes run
-        start = torch.cuda.Event(enable_timing=True)
-        start.record(main)
-        marks["start"] = start
-        copy_in.wait_event(start)              # the previous step's kernels are done with the buffers
-        copy_out.wait_event(start)
-        evs = []
-        with torch.cuda.stream(copy_in):
-            for d, h in zip(d_exc, h_exc):
-                d.copy_(h, non_blocking=True)
-            ev0 = torch.cuda.Event()
-            ev0.record(copy_in)
-            for j in range(len(cr) - 1):
-                w0, w1 = 2 * int(rb[cr[j]]), 2 * int(rb[cr[j + 1]])
-                dr.codes[w0:w1].copy_(h_own[w0 - own_w0:w1 - own_w0], non_blocking=True)
-                ev = torch.cuda.Event(enable_timing=(j == len(cr) - 2))
-                ev.record(copy_in)
-                evs.append(ev)
-            marks["h2d"] = evs[-1]
-        main.wait_event(ev0)
-        dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
-        feed = [(cr[j], cr[j + 1], (lambda j=j: main.wait_event(evs[j]))) for j in range(len(cr) - 1)]
-
-        def comp_home(comp):
-            ready = torch.cuda.Event()
-            ready.record(main)
-            with torch.cuda.stream(copy_out):
-                copy_out.wait_event(ready)
-                out_h["comp"].copy_(comp, non_blocking=True)
-
-        marks["tm"] = _EventTimers(torch)
-        r = profile_distributed(eng, k, bs, bc, "readshard_ar", table=table, pipeline_exchange=not best.endswith("/unpipelined"), xgroup=xg,
-                                feed=feed, on_comp=comp_home, peer_exchange=px if best.endswith("/p2p") else None, timers=marks["tm"])
-        marks["compute"] = torch.cuda.Event(enable_timing=True)
-        marks["compute"].record(main)
-        for kk in ("hist", "sums"):
-            out_h[kk].copy_(r[kk], non_blocking=True)
-        main.wait_stream(copy_out)
-        marks["end"] = torch.cuda.Event(enable_timing=True)
-        marks["end"].record(main)
-
-    e2e_step()
-    dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(args.steps):
-        e2e_step()
-    b.record()
-    dist.barrier()
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
-    e2e_phases = {kk: marks["start"].elapsed_time(marks[kk]) for kk in ("h2d", "compute", "end")} if "end" in marks else None
-    if e2e_phases is not None:
-        e2e_phases["phases"] = marks["tm"].phases_ms()
-    h2d = 4 * (2 * (b1 - b0)) + 8 * len(exc_blk)
-    d2h = sum(int(t.numel()) * 4 for t in out_h.values())
-
-    count_ms = phases.get("count", 0.0)
-    own_updates = valid_windows / world
-    alg = 0.375 * L * (1.0 if not best.startswith("readshard_ar") else 1.0 / world) + 16 * own_updates
-    line = {"metric": metric, "value": L / ms_step / 1e6, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"{world} x {cfg_name} shards of one community (one global 15-mer table)", "reads": n, "bases": L,
-                       "k": k, "bin_size": bs, "bins": bc, "plan": best, "plan_ms": plan_ms, "valid_15mer_windows": valid_windows,
-                       "l2_policy": "inputs larger than L2"},
-            "e2e": {"value": L / e2e_ms / 1e6, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "note": "per-rank bytes; max-over-ranks time",
-                    "rank0_ms_since_step_start": e2e_phases},
-            "gpu_launches": launches,
-            "roofline": {"kernel": "count phase on rank 0 (partition + k2_partition + k_count_smem per bucket)", "bound": "hbm", "achieved": alg / max(count_ms, 1e-6) / 1e6 / 1.0 if count_ms else None,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": (alg / max(count_ms, 1e-6) / 1e6) / hbm_peak if count_ms else None,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": count_ms, "includes": "4 GiB table memset and the key partition of this rank's rectangle"},
-            "phases_ms_rank0": phases, "clocks": clocks, "cpu_baseline": None}
-    return line
