@@ -145,6 +145,10 @@ int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_si
  *                   comfortable) add() also splits every bucket list of the chunk into 2-byte lists per 2^15-key
  *                   sub-slice, whose counters then live in one SM's shared memory; a bucket whose key skew overflows a
  *                   list's fixed share falls back to the L2-atomic kernel.  Same table either way.  Ignored without `sub`.
+ *   mode bit 3 (8): count WRITES: the table slices of the applied buckets need not be zeroed by the caller (the shared-memory
+ *                   path stores its counters instead of adding them — no 4 GiB memset, no read of the slice; the L2-atomic path
+ *                   zeroes the slices itself first).  Only for a partition that holds ALL windows of those keys (one apply per
+ *                   table); accumulating several partitions into one table (batches, chunks applied apart) needs the adding form.
  * begin() resets the lists; add() appends the windows of blocks [blk_lo, blk_hi) as one chunk (up to 64 chunks,
  * e.g. one per host-to-device copy so partitioning overlaps the transfer); build() = begin + one add.  A
  * partition can be applied several times (count, exchange tables between GPUs, then search).  Everything is

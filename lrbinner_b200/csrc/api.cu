@@ -80,7 +80,8 @@ struct lrb_ctx {
     cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr, xchg = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t sync_ev[LRB_PART_MAX_CHUNKS + 2] = {};  // [0] index arrays, [1..] H2D chunks, [last] composition D2H
-    cudaEvent_t counted = nullptr;                       // multi-GPU: this device's private counts are complete
+    cudaEvent_t counted = nullptr;                       // this device's private counts are complete
+    cudaEvent_t mirrored = nullptr;                      // the mirror pass (on the exchange stream, beside the search) is done
     cudaEvent_t sum_ev[kMaxRounds] = {}, round_ev[kMaxRounds] = {};  // exchange: my piece of round k is summed / round k has arrived here
     cudaEvent_t xev[2] = {};                             // exchange start / end (timed)
     DevBuf codes, valid, read_len, read_blk, tile_read, tile_blk;
@@ -108,6 +109,16 @@ struct lrb_ctx {
             return lrb_set_error(LRB_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// The exchange stream runs at the highest priority: its small kernels (lrb_dev_add_planes, the mirror) then get SM slots
+// ahead of the queued CTAs of the search they hide behind, instead of being stretched over the whole search
+// (measured at N = 2: k_add_planes 2.2 ms per 16 MiB piece at default priority).  LRB_XCHG_PRIO=0 turns it off.
+static cudaError_t create_xchg_stream(cudaStream_t* s) {
+    int lo = 0, hi = 0;
+    const char* e = getenv("LRB_XCHG_PRIO");
+    if ((e && atoi(e) == 0) || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+    return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+
 static int ctx_create_one(int device, lrb_ctx** out) {
     CTX_CUDA(cudaSetDevice(device));
     lrb_ctx* c = new lrb_ctx();
@@ -115,7 +126,7 @@ static int ctx_create_one(int device, lrb_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->xchg, cudaStreamNonBlocking) != cudaSuccess) {
+        create_xchg_stream(&c->xchg) != cudaSuccess) {
         const int rc = lrb_set_error(LRB_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
         lrb_ctx_destroy(c);
         return rc;
@@ -124,6 +135,7 @@ static int ctx_create_one(int device, lrb_ctx** out) {
     for (auto& ev : c->xev) cudaEventCreate(&ev);
     for (auto& ev : c->sync_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->counted, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->mirrored, cudaEventDisableTiming);
     for (auto& ev : c->sum_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto& ev : c->round_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = c;
@@ -192,6 +204,7 @@ extern "C" void lrb_ctx_destroy(lrb_ctx* c) {
     for (auto& ev : c->sum_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->round_ev) if (ev) cudaEventDestroy(ev);
     if (c->counted) cudaEventDestroy(c->counted);
+    if (c->mirrored) cudaEventDestroy(c->mirrored);
     if (c->copy_in) cudaStreamDestroy(c->copy_in);
     if (c->copy_out) cudaStreamDestroy(c->copy_out);
     if (c->xchg) cudaStreamDestroy(c->xchg);
@@ -370,7 +383,8 @@ int enqueue_upload(lrb_ctx* c, const lrb_reads* r, const Job& J, const ChunkPlan
 
 // Pass 1 of one batch.  row0 = index of the batch's first read in the caller's output arrays.  with_rids: the lists will
 // also serve the search (single-batch mode).  timed: record the phase events of lrb_ctx_last_timings.
-int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, bool with_rids, bool defer_comp, bool timed) {
+int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, bool with_rids, bool defer_comp, bool timed,
+                bool first_batch = false, bool only_batch = false) {
     CTX_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream, sin = c->copy_in, sout = c->copy_out;
     const uint64_t n = r->n_reads, nb = r->n_blocks;
@@ -386,7 +400,11 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
     if ((rc = enqueue_upload(c, r, J, ch, &ship_valid))) return rc;
     if (timed) CTX_CUDA(cudaEventRecord(c->ev[1], sin));  // H2D done
     lrb_reads_view& v = c->dview;
-    // compute stream: zero the outputs while the first chunk is in flight
+    // compute stream: zero the outputs while the first chunk is in flight.  The table is zeroed only when counts will be
+    // ADDED to it (several batches, or no lists): a device's only batch WRITES its table slices (apply mode bit 3).
+    const bool count_writes = J.do_count && lists && only_batch;
+    if (J.do_count && first_batch && !count_writes)
+        CTX_CUDA(cudaMemsetAsync(c->table.p, 0, sizeof(uint32_t) * (size_t)kTableEntries, st));
     if (J.do_comp && n) CTX_CUDA(cudaMemsetAsync(c->comp.p, 0, sizeof(uint32_t) * n * J.P, st));
     CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[0], 0));  // index arrays (and validity exceptions) are on the device
     if (!ship_valid && (rc = lrb_dev_fill_valid(&v, (const uint32_t*)c->exc_blk.p, (const uint32_t*)c->exc_valid.p, r->n_exc, st))) return rc;
@@ -420,7 +438,7 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
     CTX_CUDA(cudaEventRecord(c->sync_ev[LRB_PART_MAX_CHUNKS + 1], sout));
     if (J.do_count && lists) {
         // ONE launch over all buckets when the second-level lists exist (no per-bucket tails), else RED.ADD per bucket
-        const int mode = c->part.sub ? (1 | 4) : 1;
+        const int mode = (c->part.sub ? (1 | 4) : 1) | (count_writes ? 8 : 0);
         if ((rc = lrb_dev_partition_apply(&c->part, mode, (uint32_t*)c->table.p, J.bin_size, J.bins, nullptr, nullptr, st))) return rc;
     }
     return LRB_OK;
@@ -714,7 +732,6 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
     rc = on_devices(plans, [&](DevPlan& p) -> int {
         lrb_ctx* x = p.c;
         CTX_CUDA(cudaSetDevice(x->device));
-        if (J.do_count) CTX_CUDA(cudaMemsetAsync(x->table.p, 0, sizeof(uint32_t) * (size_t)kTableEntries, x->stream));
         const bool single = p.batches.size() == 1;
         int rc2 = LRB_OK;
         for (size_t i = 0; i < p.batches.size() && !rc2; ++i) {
@@ -723,7 +740,8 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             bool owned = false;
             if (b.r0 == 0 && b.r1 == n) s = const_cast<lrb_reads*>(r);
             else { if ((rc2 = lrb_reads_slice(r, b.r0, b.r1, &s))) break; owned = true; }
-            rc2 = stage_front(x, s, J, b.r0, /*with_rids=*/single && J.do_search, /*defer_comp=*/single && !J.comp_pinned, /*timed=*/x == c && i == 0);
+            rc2 = stage_front(x, s, J, b.r0, /*with_rids=*/single && J.do_search, /*defer_comp=*/single && !J.comp_pinned, /*timed=*/x == c && i == 0,
+                              /*first_batch=*/i == 0, /*only_batch=*/single);
             if (single && !rc2) { p.kept = s; p.kept_owned = owned; break; }
             if (!rc2) rc2 = sync_ctx(x);   // the buffers are re-used by the next batch
             if (owned) lrb_reads_free(s);
@@ -759,6 +777,19 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         };
         if (single) {
             const uint64_t nr = p.kept->n_reads;
+            // The mirror writes only the half of the table the list-driven search never reads, and it is HBM-bound where the
+            // search is bound by the L1 tag stage: it runs BESIDE the search on the (high-priority) exchange stream, after the
+            // count resp. after the last exchange round.  LRB_MIRROR_OVERLAP=0: after the search, on the same stream.
+            const bool mirror_here = J.do_count && (x == c || !J.use_part);
+            const bool mirror_beside = mirror_here && J.use_part && J.do_search && nr && p.kept->n_blocks && env_int("LRB_MIRROR_OVERLAP", 1) > 0;
+            if (mirror_beside) {
+                if (!exchanged) {
+                    CTX_CUDA(cudaEventRecord(x->counted, st));
+                    CTX_CUDA(cudaStreamWaitEvent(x->xchg, x->counted, 0));
+                }
+                if ((rc2 = lrb_dev_mirror((uint32_t*)x->table.p, x->xchg))) return rc2;
+                CTX_CUDA(cudaEventRecord(x->mirrored, x->xchg));
+            }
             if (J.do_search && nr) {
                 CTX_CUDA(cudaMemsetAsync(x->hist.p, 0, sizeof(uint32_t) * nr * (size_t)J.bins, st));
                 CTX_CUDA(cudaMemsetAsync(x->sums.p, 0, sizeof(uint32_t) * nr, st));
@@ -778,7 +809,8 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             if (rc2) return rc2;
             if (x == c) CTX_CUDA(cudaEventRecord(c->ev[3], st));  // table passes done
             // the full table (both strands) is needed on device 0 (lrb_ctx_table_save, table_host) and by the direct search
-            if (J.do_count && (x == c || !J.use_part) && (rc2 = lrb_dev_mirror((uint32_t*)x->table.p, st))) return rc2;
+            if (mirror_beside) CTX_CUDA(cudaStreamWaitEvent(st, x->mirrored, 0));
+            else if (mirror_here && (rc2 = lrb_dev_mirror((uint32_t*)x->table.p, st))) return rc2;
             if (x == c) CTX_CUDA(cudaEventRecord(c->ev[4], st));
             if (!J.use_part && J.do_search && nr &&
                 (rc2 = lrb_dev_search(&x->dview, (const uint32_t*)x->table.p, J.bin_size, J.bins, (uint32_t*)x->hist.p, (uint32_t*)x->sums.p, 0,

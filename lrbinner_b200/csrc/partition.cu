@@ -231,12 +231,20 @@ __global__ void k_chunk_scan(PartMeta* __restrict__ m, int c, int nb, ull capaci
 // copies whole runs, contiguous on both sides.  The next step's block and prelude are fetched while the current one
 // is copied out; two barriers per step.  The kernel is bound by shared-memory wavefronts (the scattered staging
 // store and the ranking atomic), so nothing else is staged.
-template <bool WITH_RID, bool FULL>
+// BULK (experiment, LRB_PART_BULK=1): the run copy-out goes through the bulk-copy engine (cp.async.bulk shared -> global,
+// SASS UBLKCP) instead of LDS + STG: every staged run starts at the same offset modulo 16 bytes as its destination, so all
+// but <= 3 entries at either end of a run move as one 16-byte-aligned bulk copy issued by one lane.
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
+template <bool WITH_RID, bool FULL, bool BULK = false>
 __global__ void __launch_bounds__(kPartThreads)
 k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, const uint32_t* __restrict__ blk_read,
             uint64_t blk_lo, uint64_t blk_hi, uint32_t key_lo, uint32_t key_hi, int shift, int nb, uint32_t n_steps, uint32_t G,
             uint32_t step0, StepTables T, const PartMeta* __restrict__ meta, int c, uint32_t* __restrict__ ent_out) {
-    __shared__ uint32_t s_ent[kStepSlots];                          // staged entries, grouped by bucket
+    __shared__ __align__(16) uint32_t s_ent[kStepSlots + (BULK ? 6 * kMaxBuckets : 0)];  // staged entries, grouped by bucket
     __shared__ uint32_t s_cur[2][kMaxBuckets];                      // staging cursor of each bucket
     __shared__ uint32_t s_beg[2][kMaxBuckets], s_n[2][kMaxBuckets]; // staged run of each bucket
     __shared__ uint32_t* s_dst[2][kMaxBuckets];                     // where the run goes in ent_out
@@ -256,14 +264,17 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
         const uint16_t* cs = T.cnt + (size_t)(step0 + s) * kMaxBuckets;
         const uint32_t c0 = (lane < nb) ? cs[lane] : 0u;
         const uint32_t c1 = (lane + 32 < nb) ? cs[lane + 32] : 0u;
-        uint32_t x0 = c0, x1 = c1;
+        // BULK: a staged run starts at its destination's offset modulo 4 entries and occupies a whole number of 16 B units
+        const uint32_t m0 = BULK ? (uint32_t)((reg0 + run0) & 3ull) : 0u, m1 = BULK ? (uint32_t)((reg1 + run1) & 3ull) : 0u;
+        const uint32_t p0 = BULK ? ((m0 + c0 + 3u) & ~3u) : c0, p1 = BULK ? ((m1 + c1 + 3u) & ~3u) : c1;
+        uint32_t x0 = p0, x1 = p1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d);
             if (lane >= d) { x0 += y0; x1 += y1; }
         }
         const uint32_t tot0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
-        const uint32_t e0 = x0 - c0, e1 = tot0 + x1 - c1;  // exclusive staging offsets
+        const uint32_t e0 = x0 - p0 + m0, e1 = tot0 + x1 - p1 + m1;  // exclusive staging offsets
         s_cur[buf][lane] = s_beg[buf][lane] = e0;
         s_cur[buf][lane + 32] = s_beg[buf][lane + 32] = e1;
         s_n[buf][lane] = c0;
@@ -310,12 +321,29 @@ k_partition(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
             fetch(s + 1, v, pv, b, rd, r0v);
             if (warp == 0) prelude(s + 1, buf ^ 1);
         }
-        for (int bk = warp; bk < nb; bk += kPartThreads / 32) {  // each warp copies whole runs: contiguous both sides
-            const uint32_t n = s_n[buf][bk];
-            const uint32_t* src = s_ent + s_beg[buf][bk];
-            uint32_t* dst = s_dst[buf][bk];
+        if (BULK) {
+            if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged entries were written by generic-proxy stores
+            for (int bk = warp; bk < nb; bk += kPartThreads / 32) {
+                const uint32_t n = s_n[buf][bk], sb = s_beg[buf][bk];
+                const uint32_t* src = s_ent + sb;
+                uint32_t* dst = s_dst[buf][bk];
+                const uint32_t head = min(n, (4u - (sb & 3u)) & 3u), body = (n - head) & ~3u, tail = n - head - body;
+                if (lane < head) __stcs(dst + lane, src[lane]);
+                if (lane < tail) __stcs(dst + head + body + lane, src[head + body + lane]);
+                if (lane == 0 && body) bulk_s2g(dst + head, src + head, body * 4u);
+            }
+            if (lane == 0) {  // the staging area is rewritten in the next step: wait until the engine has read it
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else {
+            for (int bk = warp; bk < nb; bk += kPartThreads / 32) {  // each warp copies whole runs: contiguous both sides
+                const uint32_t n = s_n[buf][bk];
+                const uint32_t* src = s_ent + s_beg[buf][bk];
+                uint32_t* dst = s_dst[buf][bk];
 #pragma unroll 2
-            for (uint32_t i = lane; i < n; i += 32) __stcs(dst + i, src[i]);
+                for (uint32_t i = lane; i < n; i += 32) __stcs(dst + i, src[i]);
+            }
         }
         __syncthreads();
     }
@@ -588,6 +616,9 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
 }
 
 // one CTA per sub-slice: its segments -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
+// OVERWRITE: the slice is WRITTEN (counts, or zeros for a bucket that falls back to k_count_keys) instead of added to, so
+// the caller needs no memset of the table and the slice is not read: -4 GiB of memset writes and -2 GiB of reads per step.
+template <bool OVERWRITE>
 __global__ void __launch_bounds__(1024)
 k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta, int bucket0, L2Layout Y, uint32_t bucket_base0, int shift,
              uint32_t* __restrict__ table) {
@@ -595,7 +626,14 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, sub = blockIdx.x;
     const int bucket = bucket0 + (int)blockIdx.y;   // one launch may cover several buckets (gridDim.y): no 1.7-wave tail per bucket
     const uint32_t bucket_base = bucket_base0 + ((uint32_t)blockIdx.y << shift);
-    if (meta->overflow || meta->overflow2[bucket]) return;
+    if (meta->overflow) return;
+    if (meta->overflow2[bucket]) {
+        if (OVERWRITE) {  // k_count_keys adds this bucket's windows to a zeroed slice
+            uint4* z4 = reinterpret_cast<uint4*>(table + bucket_base + (sub << 16));
+            for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) z4[i] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
     const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + (Y.strided ? Y.fill_pos(sub) : sub);  // + cta * nb * nsub
     const size_t fill_stride = (size_t)Y.nb * Y.nsub;
     const uint16_t* __restrict__ lists = ws + Y.bucket_base(bucket);
@@ -640,8 +678,14 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
         for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
         n = n_next;
     }
-    if (!__syncthreads_or(any)) return;  // empty sub-slice: the table slice stays as it is
     uint4* slice4 = reinterpret_cast<uint4*>(table + bucket_base + (sub << 16));
+    if (OVERWRITE) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) slice4[tid + 1024 * u] = tab4[tid + 1024 * u];
+        return;
+    }
+    if (!__syncthreads_or(any)) return;  // empty sub-slice: the table slice stays as it is
     uint4 t4[8];  // 8192 uint4 per slice, eight per thread: all loads first
 #pragma unroll
     for (int u = 0; u < 8; ++u) t4[u] = slice4[tid + 1024 * u];
@@ -662,7 +706,21 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
 constexpr uint32_t kTaskRuns = 16;
 constexpr uint32_t kBinLut = 2048;  // counts below this go through a shared-memory bin table when (B+1)*S fits
 
-template <bool USE_LUT, int U>
+// L2 eviction-priority hints (PTX createpolicy / ld.global.L2::cache_hint): HINT = 1 marks the table gathers evict_last
+// (the 32 MiB slice of the current bucket should outlive the 312 MB entry stream and the histogram REDs that pass
+// through L2 beside it); the entry stream is already evict-first (__ldcs).  Kept or rejected on measured DRAM bytes.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ldg_hint(const uint32_t* a, uint64_t pol) {
+    uint32_t v;
+    asm("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+
+template <bool USE_LUT, int U, int HINT = 0>
 __global__ void __launch_bounds__(256)
 k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket0, int n_chunks, ChunkList L,
               StepTables T, uint32_t bucket_base0, uint32_t hi_mask2, int shift, const uint32_t* __restrict__ table, uint32_t S32,
@@ -683,6 +741,8 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
     }
     const uint32_t lane = threadIdx.x & 31u, wl = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint64_t pol = HINT ? l2_policy_evict_last() : 0ull;
+    auto gather = [&](uint32_t key) { return HINT ? ldg_hint(table + key, pol) : table[key]; };
     const uint32_t* __restrict__ off_row = T.off + (size_t)bucket * T.cap;
     uint32_t* bnd = s_bnd[wl];
     uint32_t* r0 = s_r0[wl];
@@ -722,7 +782,7 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
             for (int u = 0; u < U; ++u) e[u] = __ldcs(src + 32 * u);
             for (;;) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) cn[u] = table[entry_key(e[u], bucket_base, hi_mask2)];
+                for (int u = 0; u < U; ++u) cn[u] = gather(entry_key(e[u], bucket_base, hi_mask2));
                 const bool more = i0 + 2u * kStep <= span_end;  // warp-uniform
                 if (more) {
                     const uint32_t* nsrc = region + i0 + kStep + lane;
@@ -740,8 +800,8 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
         for (; i0 + 128u <= span_end; i0 += 128u) {  // (U > 4) full 128-entry steps that are left
             const uint32_t* src = region + i0 + lane;
             const uint32_t e0 = __ldcs(src), e1 = __ldcs(src + 32), e2 = __ldcs(src + 64), e3 = __ldcs(src + 96);
-            const uint32_t c0 = table[entry_key(e0, bucket_base, hi_mask2)], c1 = table[entry_key(e1, bucket_base, hi_mask2)],
-                           c2 = table[entry_key(e2, bucket_base, hi_mask2)], c3 = table[entry_key(e3, bucket_base, hi_mask2)];
+            const uint32_t c0 = gather(entry_key(e0, bucket_base, hi_mask2)), c1 = gather(entry_key(e1, bucket_base, hi_mask2)),
+                           c2 = gather(entry_key(e2, bucket_base, hi_mask2)), c3 = gather(entry_key(e3, bucket_base, hi_mask2));
             emit(e0, c0, i0 + lane, true);
             emit(e1, c1, i0 + lane + 32u, true);
             emit(e2, c2, i0 + lane + 64u, true);
@@ -757,7 +817,7 @@ k_search_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ me
                 e[u] = act[u] ? __ldcs(region + i) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? table[entry_key(e[u], bucket_base, hi_mask2)] : 0u;
+            for (int u = 0; u < 4; ++u) cnt[u] = act[u] ? gather(entry_key(e[u], bucket_base, hi_mask2)) : 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (i0 + 32u * u >= span_end) break;  // warp-uniform
@@ -889,10 +949,13 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
         LRB_LAUNCH("k_step_hist", st, k_step_hist<false><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T));
     LRB_LAUNCH("k_group_scan", st, k_group_scan<<<nb, 256, 0, st>>>(T, n_groups, meta, c));
     LRB_LAUNCH("k_chunk_scan", st, k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity));
-#define LRB_LAUNCH_PART(RID, FULLK)                                                                                                   \
-    LRB_LAUNCH("k_partition", st, k_partition<RID, FULLK><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, \
+#define LRB_LAUNCH_PART(RID, FULLK, ...)                                                                                              \
+    LRB_LAUNCH("k_partition", st, k_partition<RID, FULLK, ##__VA_ARGS__><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, \
                                                                shift, nb, n_steps, G, step0, T, meta, c, part->keys))
-    if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
+    static const bool bulk = getenv("LRB_PART_BULK") && atoi(getenv("LRB_PART_BULK")) > 0;   // experiment: copy-out by cp.async.bulk
+    if (bulk && full && part->has_rids) LRB_LAUNCH_PART(true, true, true);
+    else if (bulk && full) LRB_LAUNCH_PART(false, true, true);
+    else if (part->has_rids) { if (full) LRB_LAUNCH_PART(true, true); else LRB_LAUNCH_PART(true, false); }
     else { if (full) LRB_LAUNCH_PART(false, true); else LRB_LAUNCH_PART(false, false); }
 #undef LRB_LAUNCH_PART
     if (part->l2_enabled) {
@@ -973,6 +1036,7 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     const bool do_count = mode & 1, do_search = mode & 2;
     // second-level (shared-memory) counting needs the sub-slice lists built by add(); without them the L2-atomic kernel does the job
     const bool smem_count = do_count && (mode & 4) && part->l2_enabled;
+    const bool overwrite = do_count && (mode & 8);   // the caller did not zero the slices of the applied buckets
     L2Layout Y = {0, 0, 0, 0, 0, 0, 0, 0};
     if (smem_count) {
         Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
@@ -1006,38 +1070,49 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     // the gathers for the memory pipe), kept behind LRB_SEARCH_LUT=1 for experiments
     const char* lut_env = getenv("LRB_SEARCH_LUT");
     const bool use_lut = lut_env && atoi(lut_env) > 0 && ((uint64_t)bins + 1) * S32 < kBinLut;
+    const char* hint_env = getenv("LRB_SEARCH_HINT");   // 1: evict_last on the table gathers (experiment, see k_search_keys)
+    const bool hint = hint_env && atoi(hint_env) > 0;
     const char* un_env = getenv("LRB_SEARCH_UNROLL");  // gathers in flight per lane: 8 (default, 22.3 ms at config #2) or 4 (23.7 ms)
     const bool unroll8 = !(un_env && atoi(un_env) == 4);
     constexpr int kSmemTable = (1 << kSubBits) * (int)sizeof(uint32_t);
-    if (smem_count) LRB_CUDA(cudaFuncSetAttribute(k_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
+    if (smem_count) {
+        LRB_CUDA(cudaFuncSetAttribute(k_count_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
+        LRB_CUDA(cudaFuncSetAttribute(k_count_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTable));
+    }
+    if (overwrite && !smem_count && bucket_hi > bucket_lo)   // the L2-atomic kernel adds: zero the slices of these buckets here
+        LRB_CUDA(cudaMemsetAsync(table + part->key_lo + ((size_t)bucket_lo << part->shift), 0, sizeof(uint32_t) * ((size_t)(bucket_hi - bucket_lo) << part->shift), st));
     const bool count_batched = do_count && smem_count && !do_search && bucket_hi > bucket_lo;
     if (count_batched) {  // count only: every bucket in one launch each of the two kernels (the second only counts flagged buckets)
         const uint32_t base0 = part->key_lo + ((uint32_t)bucket_lo << shift);
         const dim3 g1(Y.nsub, (unsigned)(bucket_hi - bucket_lo)), g2(grid, (unsigned)(bucket_hi - bucket_lo));
-        LRB_LAUNCH("k_count_smem", st, k_count_smem<<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table));
+        if (overwrite) LRB_LAUNCH("k_count_smem", st, k_count_smem<true><<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table));
+        else LRB_LAUNCH("k_count_smem", st, k_count_smem<false><<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table));
         LRB_LAUNCH("k_count_keys", st, k_count_keys<<<g2, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, base0, shift, hi_mask2, table, 1));
     }
     const bool search_batched = do_search && !do_count && bucket_hi > bucket_lo;
     if (search_batched) {
         const uint32_t base0 = part->key_lo + ((uint32_t)bucket_lo << shift);
         const dim3 gs(sgrid, (unsigned)(bucket_hi - bucket_lo));
-#define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
-    LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN><<<gs, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, L, T, base0, hi_mask2, shift, table, S32, magic, \
+#define LRB_LAUNCH_SEARCH(LUT, UN, ...)                                                                                                \
+    LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN, ##__VA_ARGS__><<<gs, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, L, T, base0, hi_mask2, shift, table, S32, magic, \
                                                (uint32_t)bins, hist))
         if (use_lut) LRB_LAUNCH_SEARCH(true, 4);
+        else if (unroll8 && hint) LRB_LAUNCH_SEARCH(false, 8, 1);
         else if (unroll8) LRB_LAUNCH_SEARCH(false, 8);
         else LRB_LAUNCH_SEARCH(false, 4);
 #undef LRB_LAUNCH_SEARCH
     }
     for (int b = bucket_lo; b < bucket_hi && !count_batched && !search_batched; ++b) {
         const uint32_t bucket_base = part->key_lo + ((uint32_t)b << shift);
-        if (smem_count) LRB_LAUNCH("k_count_smem", st, k_count_smem<<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table));
+        if (smem_count && overwrite) LRB_LAUNCH("k_count_smem", st, k_count_smem<true><<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table));
+        else if (smem_count) LRB_LAUNCH("k_count_smem", st, k_count_smem<false><<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table));
         if (do_count) LRB_LAUNCH("k_count_keys", st, k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, shift, hi_mask2, table, smem_count ? 1 : 0));
         if (do_search) {
-#define LRB_LAUNCH_SEARCH(LUT, UN)                                                                                                     \
-    LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \
+#define LRB_LAUNCH_SEARCH(LUT, UN, ...)                                                                                                \
+    LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN, ##__VA_ARGS__><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \
                                                   (uint32_t)bins, hist))
             if (use_lut) LRB_LAUNCH_SEARCH(true, 4);
+            else if (unroll8 && hint) LRB_LAUNCH_SEARCH(false, 8, 1);
             else if (unroll8) LRB_LAUNCH_SEARCH(false, 8);
             else LRB_LAUNCH_SEARCH(false, 4);
 #undef LRB_LAUNCH_SEARCH

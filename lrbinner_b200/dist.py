@@ -67,6 +67,7 @@ class CudaEngine:
         self.ws = profile.PartitionWorkspace(device_reads, capacity=workspace_entries)
         self._rect = None
         self._verified = set()
+        self.can_overwrite = True                   # count(..., overwrite=True) writes the table slices: no table.zero_() needed
 
     def zeros(self, shape):
         return self.torch.zeros(shape, dtype=self.torch.int32, device=self.device)
@@ -91,12 +92,12 @@ class CudaEngine:
         tlo, thi = self.dr.tile_range_for_reads(read_lo, read_hi)
         self.p.dev_composition(self.dr, k, comp, tlo, thi)
 
-    def count(self, table, key_lo, key_hi, read_lo, read_hi):
+    def count(self, table, key_lo, key_hi, read_lo, read_hi, overwrite=False):
         self._rect = None                            # new step: the reads may have been re-uploaded
         self._partition(read_lo, read_hi, key_lo, key_hi)
-        self.ws.apply(table, count=True)
+        self.ws.apply(table, count=True, overwrite=overwrite)
 
-    def count_fed(self, table, read_lo, read_hi, chunks, per_chunk):
+    def count_fed(self, table, read_lo, read_hi, chunks, per_chunk, overwrite=False):
         """count() over the whole key space with the reads arriving in chunks (the e2e pipeline: the partition of chunk j
         runs while chunk j+1 is still on PCIe).  chunks = [(read_lo_j, read_hi_j), ...] covering [read_lo, read_hi);
         per_chunk(j) is called before chunk j is touched (it makes the stream wait for the chunk and may run other
@@ -125,7 +126,7 @@ class CudaEngine:
                 self.ws.build(True, blo, bhi, 0, self.table_entries, self.shift, grow=True, count=True)
             self._verified.add(rect)
         self._rect = rect
-        self.ws.apply(table, count=True)
+        self.ws.apply(table, count=True, overwrite=overwrite)
         stamp("applied")
         if dbg:
             self.torch.cuda.synchronize()
@@ -276,7 +277,10 @@ class PeerExchange:
         self.peers = [(self.rank + d) % self.world for d in range(1, self.world)]  # rotated: no two ranks start on the same peer
         self.peer_table = {p: self.hdl.get_buffer(p, (entries,), torch.int32) for p in self.peers}
         self.stage = None
-        self.comm = torch.cuda.Stream(device=device)
+        # highest priority: k_add_planes / the mirror get SM slots ahead of the queued CTAs of the search they hide behind
+        # (at default priority every 16 MiB add took 2.2 ms at N = 2, stretching the exchange over the whole search)
+        prio = -1 if os.environ.get("LRB_XCHG_PRIO", "1") != "0" else 0
+        self.comm = torch.cuda.Stream(device=device, priority=prio)
 
     def run(self, engine, table, bin_size, bins, hist_all, sums_all, lo, hi):
         """table (== self.table) holds this rank's private canonical counts; on return it holds the global, mirrored table
@@ -397,19 +401,23 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
     comp = comp_all[lo:hi]
     mark("composition")
 
+    # plan X on an engine whose count WRITES the table (every canonical slice, from one partition of all own windows): no
+    # 4 GiB memset; the non-canonical half is written by the mirror
+    ow = plan == "readshard_ar" and hi > lo and getattr(engine, "can_overwrite", False) and table is not None
     if table is None:
         table = engine.zeros((entries,))
-    else:
+    elif not ow:
         table.zero_()
+    kw_ow = {"overwrite": True} if ow else {}
     pipelined = plan == "readshard_ar" and pipeline_exchange and hasattr(engine, "search_slice") and getattr(engine, "canon_bit", None) is not None
     if plan == "readshard_ar":
         if fed:
             def per_chunk(j):
                 feed[j][2]()
                 engine.composition(k, comp_all, feed[j][0], feed[j][1])
-            engine.count_fed(table, lo, hi, [(a, b) for a, b, _ in feed], per_chunk)
+            engine.count_fed(table, lo, hi, [(a, b) for a, b, _ in feed], per_chunk, **kw_ow)
         elif hi > lo:
-            engine.count(table, 0, entries, lo, hi)
+            engine.count(table, 0, entries, lo, hi, **kw_ow)
         mark("count")
         if on_comp is not None:      # the composition rows are final: the caller may start taking them home
             on_comp(comp)

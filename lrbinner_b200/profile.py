@@ -356,10 +356,12 @@ class PartitionWorkspace:
         return int(needed.value)
 
     def apply(self, table, count=True, search=False, bin_size=1, bins=1, hist=None, sums=None, smem_count=True,
-              bucket_lo=0, bucket_hi=None):
+              bucket_lo=0, bucket_hi=None, overwrite=False):
         """smem_count: count through the second-level, shared-memory path (falls back per bucket on key skew).
-        bucket_lo/bucket_hi: only these buckets (sums are rewritten by the call that includes the last one)."""
-        mode = (1 if count else 0) | (2 if search else 0) | (4 if (count and smem_count) else 0)
+        bucket_lo/bucket_hi: only these buckets (sums are rewritten by the call that includes the last one).
+        overwrite: the count WRITES the table slices of the applied buckets (no memset by the caller; this partition must
+        hold all windows of those keys)."""
+        mode = (1 if count else 0) | (2 if search else 0) | (4 if (count and smem_count) else 0) | (8 if (count and overwrite) else 0)
         check(lib.lrb_dev_partition_apply_range(C.byref(self.part), mode, bucket_lo, 64 if bucket_hi is None else bucket_hi,
                                                 C.c_void_p(table.data_ptr()), bin_size, bins,
                                                 C.c_void_p(hist.data_ptr()) if hist is not None else None,

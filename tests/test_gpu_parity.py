@@ -503,6 +503,23 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
         table_p = z(2 ** 30)
         dev_table15_partitioned(dr, ws, table_p, True, **kw)
         assert torch.equal(table_p, table_d), kw
+    # the WRITING form of the count (apply mode bit 3: no memset by the caller): a table full of garbage comes out as the
+    # counts in its canonical half — through the shared-memory path, the L2-atomic path, and a per-bucket-range apply
+    garbage = lambda: torch.full((2 ** 30,), -559038737, dtype=torch.int32, device=DEV)
+    canon = lambda t: t.view(-1, 2, 1 << 15)[:, 0, :]
+    for kw in (dict(smem_count=True), dict(smem_count=False)):
+        table_p = garbage()
+        ws.build(True)
+        ws.apply(table_p, count=True, overwrite=True, **kw)
+        assert torch.equal(canon(table_p), canon(table_d)), kw
+    table_p = garbage()
+    ws.build(True, log2_bucket_keys=25)
+    for lo, hi in ((0, 5), (5, 6), (6, 32)):
+        ws.apply(table_p, count=True, overwrite=True, bucket_lo=lo, bucket_hi=hi)
+    dev_mirror(table_p)                                    # the mirror writes every entry of the other half
+    table_m = table_d.clone()
+    dev_mirror(table_m)
+    assert torch.equal(table_p, table_m)
     # barely enough room for the second-level lists: many (bucket, sub-slice, CTA) segments overflow and their buckets fall
     # back to the L2-atomic kernel, the others go through shared memory — one table
     tiny = PartitionWorkspace(dr, sub_capacity=int(1.3 * ws.capacity) + (1 << 20))
@@ -510,6 +527,10 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     dev_table15_partitioned(dr, tiny, table_p, True)
     dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=25)
     assert torch.equal(table_p, 2 * table_d + 7)
+    table_p = garbage()                                    # ... and the writing form zeroes the slices of the buckets that fall back
+    tiny.build(True)
+    tiny.apply(table_p, count=True, overwrite=True)
+    assert torch.equal(canon(table_p), canon(table_d))
     del tiny
     # workspace too small is an error, not a truncation
     small = PartitionWorkspace(dr, capacity=1000)
@@ -564,6 +585,12 @@ def test_second_level_count_survives_key_skew():
             o2 = ws.small[2 * 64 * 64 + 65 + 2:2 * 64 * 64 + 65 + 2 + 32].cpu().numpy().view(np.uint32)
             fell_back[shift] = int(o2[:ws.part.n_buckets].astype(bool).sum())
         assert torch.equal(table_p, table_d), shift
+        if shift != 22:                                    # the same mix of paths, writing instead of adding
+            table_w = torch.full((2 ** 30,), 123456789, dtype=torch.int32, device=DEV)
+            ws.build(True, log2_bucket_keys=shift)
+            ws.apply(table_w, count=True, overwrite=True)
+            assert torch.equal(table_w.view(-1, 2, 1 << 15)[:, 0, :], table_d.view(-1, 2, 1 << 15)[:, 0, :]), shift
+            del table_w
     # the homopolymer bucket must have fallen back; most buckets must not have (they took the overflow-list path at worst)
     assert 1 <= fell_back[24] <= 32, fell_back
 
