@@ -779,11 +779,12 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         };
         if (single) {
             const uint64_t nr = p.kept->n_reads;
-            // The mirror writes only the half of the table the list-driven search never reads, and it is HBM-bound where the
-            // search is bound by the L1 tag stage: it runs BESIDE the search on the (high-priority) exchange stream, after the
-            // count resp. after the last exchange round.  LRB_MIRROR_OVERLAP=0: after the search, on the same stream.
+            // The mirror writes only the half of the table the list-driven search never reads, so it COULD run beside the
+            // search (LRB_MIRROR_OVERLAP=1: on the exchange stream, after the count resp. the last exchange round).  Measured
+            // and rejected as the default (profiles/r02_exp1_variants.jsonl): the 4 GiB it streams through L2 evict the
+            // search's resident table slice — the search goes from 20.5 to 26.2 ms to hide a 1.26 ms pass.
             const bool mirror_here = J.do_count && (x == c || !J.use_part);
-            const bool mirror_beside = mirror_here && J.use_part && J.do_search && nr && p.kept->n_blocks && env_int("LRB_MIRROR_OVERLAP", 1) > 0;
+            const bool mirror_beside = mirror_here && J.use_part && J.do_search && nr && p.kept->n_blocks && env_int("LRB_MIRROR_OVERLAP", 0) > 0;
             if (mirror_beside) {
                 if (!exchanged) {
                     CTX_CUDA(cudaEventRecord(x->counted, st));

@@ -279,6 +279,7 @@ class PeerExchange:
         self.stage = None
         # highest priority: k_add_planes / the mirror get SM slots ahead of the queued CTAs of the search they hide behind
         # (at default priority every 16 MiB add took 2.2 ms at N = 2, stretching the exchange over the whole search)
+        self.mirror_beside = os.environ.get("LRB_MIRROR_OVERLAP", "0") != "0"
         prio = -1 if os.environ.get("LRB_XCHG_PRIO", "1") != "0" else 0
         self.comm = torch.cuda.Stream(device=device, priority=prio)
 
@@ -335,13 +336,18 @@ class PeerExchange:
                 ev = torch.cuda.Event()
                 ev.record(comm)
                 events.append(ev)
-            engine.mirror_on(table, comm)                     # non-canonical half: never read by the search
+            if self.mirror_beside:
+                engine.mirror_on(table, comm)                 # non-canonical half: never read by the search
             self.hdl.barrier()                                # (the next step refills the tables only after everybody is here)
         for k, ev in enumerate(events):
             main.wait_event(ev)
             if hi > lo:                                       # the round's buckets are contiguous: one launch
                 engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, pieces[rounds[k][0][0]][0], pieces[rounds[k][-1][0]][1])
         main.wait_stream(comm)
+        if not self.mirror_beside:
+            # after the search, not beside it: the mirror streams 4 GiB through L2 and evicts the search's resident table
+            # slice (single GPU, profiles/r02_exp1_variants.jsonl: search 20.5 -> 26.2 ms with the mirror beside it)
+            engine.mirror(table)
 
 
 _SIDE = {}

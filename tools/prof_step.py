@@ -23,10 +23,10 @@ hist = torch.zeros((n, 10), dtype=torch.int32, device=dev)
 sums = torch.zeros(n, dtype=torch.int32, device=dev)
 ws = PartitionWorkspace(dr)
 for _ in range(a.steps):
-    comp.zero_(); table.zero_(); hist.zero_(); sums.zero_()
+    comp.zero_(); hist.zero_(); sums.zero_()          # the table is WRITTEN by the count (apply mode bit 3): no memset
     dev_composition(dr, k, comp)
     ws.build(True, log2_bucket_keys=a.bucket_log2)
-    ws.apply(table, count=True)
+    ws.apply(table, count=True, overwrite=True)
     ws.apply(table, count=False, search=True, bin_size=32, bins=10, hist=hist, sums=sums)
     dev_mirror(table)
 torch.cuda.synchronize()
