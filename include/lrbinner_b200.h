@@ -143,8 +143,10 @@ int lrb_dev_search(const lrb_reads_view* dev, const uint32_t* table, long bin_si
  *   mode 3  both  : per bucket count, then search      (single-GPU fused path)
  *   mode bit 2 (4): count through shared memory.  When `sub` is given (sub_capacity u16 entries, >= ~1.3 x capacity; 2 x is
  *                   comfortable) add() also splits every bucket list of the chunk into 2-byte lists per 2^15-key
- *                   sub-slice, whose counters then live in one SM's shared memory; a bucket whose key skew overflows a
- *                   list's fixed share falls back to the L2-atomic kernel.  Same table either way.  Ignored without `sub`.
+ *                   sub-slice, whose counters then live in one SM's shared memory.  Entries that find their list's fixed share
+ *                   full (hot keys of low-complexity reads) go to a spill area (1/8 of the capacity) and are applied with
+ *                   warp-aggregated REDs; only if that fills up does a bucket fall back to the L2-atomic kernel.  Same table
+ *                   either way.  Ignored without `sub`.
  *   mode bit 3 (8): count WRITES: the table slices of the applied buckets need not be zeroed by the caller (the shared-memory
  *                   path stores its counters instead of adding them — no 4 GiB memset, no read of the slice; the L2-atomic path
  *                   zeroes the slices itself first).  Only for a partition that holds ALL windows of those keys (one apply per
@@ -179,6 +181,8 @@ typedef struct {
     int l2_enabled;                /* second-level lists are being built (filled by begin()) */
     uint32_t l2_ncta, l2_C3;
     uint64_t l2_seg0, l2_span;
+    uint64_t l2_spill0;            /* spill area of the second level (hot keys), u16 offset in `sub` */
+    uint32_t l2_spill_cap;         /* ... and its capacity in entries */
 } lrb_partition;
 uint64_t lrb_partition_step_capacity(uint64_t n_blocks, int max_chunks);
 uint64_t lrb_partition_steps_words(uint64_t step_capacity);

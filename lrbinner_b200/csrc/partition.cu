@@ -61,7 +61,9 @@ struct PartMeta {
     ull chunk_base[kMaxChunks + 1];        // first entry of each chunk's region
     ull needed;                            // entries the chunks added so far need in total
     ull overflow;                          // != 0: capacity exceeded, lists are incomplete (apply does nothing)
-    uint32_t overflow2[kMaxBuckets];       // second level: a sub list of bucket b overflowed -> k_count_keys counts b
+    uint32_t overflow2[kMaxBuckets];       // second level: bucket b could not be listed (spill area full) -> k_count_keys counts b
+    ull spill_n;                           // entries in the spill area (second level: rows / segments that overflowed)
+    ull spill_dropped;                     // != 0: the spill area itself overflowed (its buckets are flagged in overflow2)
 };
 static_assert(sizeof(PartMeta) <= sizeof(ull) * LRB_PART_SMALL_U64, "lrb_partition.small too small");
 
@@ -359,6 +361,14 @@ __device__ __forceinline__ uint32_t entry_key(uint32_t e, uint32_t bucket_base, 
     return bucket_base | (e & 0x7FFFu) | ((e << 1) & hi_mask2);
 }
 
+// one RED per distinct key of the warp's 32 entries: equal keys come in runs when a read is a homopolymer or a tandem
+// repeat, and same-address atomics serialise (profiles/r02_exp_skew_*.jsonl)
+__device__ __forceinline__ void red_aggregated(uint32_t* __restrict__ table, uint32_t key, bool active) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, active ? key : (0xFFFFFFE0u | lane));   // inactive lanes match nobody (keys are < 2^30)
+    if (active && (uint32_t)__ffs(peers) - 1u == lane) atomicAdd(table + key, (uint32_t)__popc(peers));
+}
+
 __global__ void __launch_bounds__(256)
 k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ meta, int bucket0, int n_chunks, uint32_t bucket_base0,
              int shift, uint32_t hi_mask2, uint32_t* __restrict__ table, int fallback_only) {
@@ -367,6 +377,18 @@ k_count_keys(const uint32_t* __restrict__ ents, const PartMeta* __restrict__ met
     if (meta->overflow) return;
     if (fallback_only && !meta->overflow2[bucket]) return;  // the shared-memory path counted this bucket
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    if (fallback_only) {   // a bucket that could not be listed is a key-skewed one: aggregate equal keys (warp-uniform loop)
+        for (int c = 0; c < n_chunks; ++c) {
+            const uint64_t n = meta->counts[c][bucket];
+            const uint32_t* __restrict__ ee = ents + meta->offsets[c][bucket];
+            for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); i0 < n; i0 += stride) {
+                const uint64_t i = i0 + (threadIdx.x & 31u);
+                const bool act = i < n;
+                red_aggregated(table, act ? entry_key(__ldcs(ee + i), bucket_base, hi_mask2) : 0u, act);
+            }
+        }
+        return;
+    }
     for (int c = 0; c < n_chunks; ++c) {
         const uint64_t n = meta->counts[c][bucket];
         const uint32_t* __restrict__ ee = ents + meta->offsets[c][bucket];
@@ -419,6 +441,16 @@ struct L2Layout {
     __host__ __device__ uint32_t fill_pos(uint32_t sub) const { return (sub & 15u) * (nsub >> 4) + (sub >> 4); }
     uint64_t seg0, span;            // first segment; u16 units per bucket (its segments + a spare tile)
     __host__ __device__ uint64_t bucket_base(uint32_t b) const { return seg0 + (uint64_t)b * span; }
+    // spill area: full table keys (u32) of the entries that found their staging row, the tile's overflow list or their
+    // segment full (hot keys: low-complexity reads put thousands of equal windows into one tile); applied with warp-
+    // aggregated REDs by k_count_spill after the shared-memory count
+    uint64_t spill0;                // u16 offset of the area in the workspace
+    uint32_t spill_cap;             // entries
+    uint32_t key_lo;                // first key of bucket 0
+    int shift;
+    __host__ __device__ uint32_t key_of(uint32_t bucket, uint32_t sub, uint32_t low15) const {
+        return key_lo + (bucket << shift) + (sub << 16) + low15;
+    }
 };
 
 template <int LOG2_NSUB, bool STRIDED>
@@ -429,6 +461,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     __shared__ uint32_t s_cnt[kMaxSubs];           // entries of the tile per sub-slice (zero between tiles)
     __shared__ uint32_t s_ovl[kL2Ovl];             // (sub << 15) | low key bits of the entries that found their row full
     __shared__ uint32_t s_novl[2];                 // length of s_ovl, by tile parity
+    __shared__ uint32_t s_sp2[kMaxSubs];           // entries of the tile per sub-slice that went straight to the spill area (rare)
     __shared__ uint32_t s_tiles[kMaxBuckets], s_runs[kMaxBuckets], s_start[kMaxBuckets], s_runs0[kMaxBuckets];  // tile schedule (below)
     __shared__ ull s_reg_n[kMaxBuckets], s_reg_off[kMaxBuckets];
     __shared__ uint32_t s_ovf[kMaxBuckets];
@@ -438,7 +471,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     constexpr uint32_t spw = nsub / kL2Warps;      // sub-slices (staging rows) owned by a warp (nsub >= 16)
     if (meta->overflow) return;  // lists incomplete: nothing is applied anywhere
     uint32_t* __restrict__ fill = reinterpret_cast<uint32_t*>(ws) + (size_t)blockIdx.x * Y.nb * nsub;  // this CTA's row
-    for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) s_cnt[i] = 0;
+    for (uint32_t i = tid; i < (uint32_t)kMaxSubs; i += kL2Threads) { s_cnt[i] = 0; s_sp2[i] = 0; }
     const uint32_t n_cta = gridDim.x;
     if (tid < (uint32_t)kMaxBuckets) {
         s_ovf[tid] = 0;
@@ -507,6 +540,21 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         }
     };
     const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
+    uint32_t* __restrict__ spill_keys = reinterpret_cast<uint32_t*>(ws + Y.spill0);
+    // n keys of this warp into the spill area: one reservation per call (warp-aggregated), keys produced by key_at(i).
+    // When the area is full the remaining keys are dropped and the bucket is flagged: k_count_keys then counts the whole
+    // bucket from the first-level list and both other count kernels skip it.
+    auto spill_warp = [&](uint32_t n, uint32_t bucket, auto key_at) {   // called by all lanes of a warp with equal arguments
+        ull base = 0;
+        if (lane == 0) base = atomicAdd(&meta->spill_n, (ull)n);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base + n > (ull)Y.spill_cap) {
+            if (lane == 0) { s_ovf[bucket] = 1u; meta->spill_dropped = 1ull; }
+            if (base >= (ull)Y.spill_cap) return;
+            n = (uint32_t)((ull)Y.spill_cap - base);
+        }
+        for (uint32_t i = lane; i < n; i += 32) spill_keys[base + i] = key_at(i);
+    };
     // lane j < spw of a warp looks after row / fill counter j of the warp's sub-slices.  STRIDED (default): the warp owns
     // sub-slices warp + 16 j — measured 2 ms faster per step than the blocked ownership 16 warp + j (LRB_K2_ROWS=block)
     const uint32_t my_sub = STRIDED ? warp + (uint32_t)kL2Warps * lane : warp * spw + lane;
@@ -538,12 +586,37 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             for (int j = 0; j < kL2PerThread; ++j)
                 if (j * kL2Threads + tid < n_cur) place(j);
         }
+        uint32_t spill2 = 0;   // entries that missed the overflow list as well: straight to the spill area
         if (spill) {
 #pragma unroll
             for (int j = 0; j < kL2PerThread; ++j) {
                 if ((spill >> j) & 1u) {
                     const uint32_t o = atomicAdd(&s_novl[par], 1u);
                     if (o < (uint32_t)kL2Ovl) s_ovl[o] = e[j] & stage_mask;
+                    else spill2 |= 1u << j;
+                }
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, spill2 != 0u)) {   // rare: a hot key filled row + overflow list of this tile
+            const uint32_t mine = (uint32_t)__popc(spill2);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += y;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            ull base = 0;
+            if (lane == 0) base = atomicAdd(&meta->spill_n, (ull)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0) + (incl - mine);
+            if (base + mine > (ull)Y.spill_cap) { s_ovf[b_cur] = 1u; meta->spill_dropped = 1ull; }
+#pragma unroll
+            for (int j = 0; j < kL2PerThread; ++j) {
+                if ((spill2 >> j) & 1u) {
+                    const uint32_t sub = (e[j] >> kSubBits) & sub_mask;
+                    if (base < (ull)Y.spill_cap) spill_keys[base] = Y.key_of(b_cur, sub, e[j] & 0x7FFFu);
+                    ++base;
+                    atomicAdd(&s_sp2[sub], 1u);   // the row's list entry count excludes these
                 }
             }
         }
@@ -556,7 +629,11 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         // goes (a 32-bit position inside the bucket's span) and how much of it; the copy loop is then two predicated
         // 2-byte copies per row (the expected row holds 8192 / nsub = cap / 4 entries)
         const uint32_t novl_raw = s_novl[par];
-        const uint32_t n_my = lane < spw ? s_cnt[my_sub] : 0u;
+        uint32_t n_my = lane < spw ? s_cnt[my_sub] : 0u;   // entries of the tile ranked into this row ...
+        if (novl_raw > (uint32_t)kL2Ovl && lane < spw) {   // ... minus those that left through the spill area (warp-uniform test)
+            const uint32_t gone = s_sp2[my_sub];
+            if (gone) { n_my -= gone; s_sp2[my_sub] = 0; }
+        }
         const bool ok_my = f_my + n_my <= Y.C3;   // a full segment takes nothing more (its bucket falls back)
         uint32_t ns_my = 0, off_my = 0;
         if (lane < spw && n_my) {
@@ -565,13 +642,35 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
                 frow[my_pos] = f_my + n_my;
                 ns_my = min(n_my, cap);
                 off_my = Y.seg(my_sub, blockIdx.x) * Y.C3 + f_my;   // < 2^32 (lrb_dev_partition_begin clamps C3)
-            } else {
-                s_ovf[b_cur] = 1u;
             }
         }
-        if (tid == 0) {
-            s_novl[par ^ 1u] = 0;  // the next tile's list; last read before the previous tile's closing barrier
-            if (novl_raw > (uint32_t)kL2Ovl) s_ovf[b_cur] = 1u;  // entries were dropped: k_count_keys counts this bucket
+        if (tid == 0) s_novl[par ^ 1u] = 0;  // the next tile's list; last read before the previous tile's closing barrier
+        // rows whose segment is full (a hot sub-slice: more than C3 entries from this CTA): staged part and overflow-list
+        // part go to the spill area
+        const uint32_t full_rows = __ballot_sync(0xFFFFFFFFu, lane < spw && n_my != 0u && !ok_my);
+        for (uint32_t rest = full_rows; rest; rest &= rest - 1u) {
+            const uint32_t jj = (uint32_t)__ffs(rest) - 1u;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, n_my, jj);
+            const uint32_t sub = (STRIDED ? warp + (uint32_t)kL2Warps * jj : warp * spw + jj);
+            const uint16_t* src = s_stage + (sub << cap_shift);
+            const uint32_t bkt = b_cur;
+            spill_warp(min(n, cap), bkt, [&](uint32_t i) { return Y.key_of(bkt, sub, src[(i + 2u * sub) & (cap - 1u)] & 0x7FFFu); });
+            if (n > cap) {
+                const uint32_t novl = min(novl_raw, (uint32_t)kL2Ovl);
+                for (uint32_t i0 = 0; i0 < novl; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const uint32_t r = i < novl ? s_ovl[i] : 0xFFFFFFFFu;
+                    const bool mine = i < novl && (r >> kSubBits) == sub;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (!bal) continue;
+                    const uint32_t cnt = (uint32_t)__popc(bal), pos = (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    ull base = 0;
+                    if (lane == 0) base = atomicAdd(&meta->spill_n, (ull)cnt);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (base + cnt > (ull)Y.spill_cap && lane == 0) { s_ovf[bkt] = 1u; meta->spill_dropped = 1ull; }
+                    if (mine && base + pos < (ull)Y.spill_cap) spill_keys[base + pos] = Y.key_of(bkt, sub, r & 0x7FFFu);
+                }
+            }
         }
         uint16_t* __restrict__ lists = ws + Y.bucket_base(b_cur);
         constexpr uint32_t cm = cap - 1u;
@@ -613,6 +712,28 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     }
     __syncthreads();
     if (tid < Y.nb && s_ovf[tid]) meta->overflow2[tid] = 1u;
+}
+
+// the spill area of k2_partition: full table keys of hot rows -> warp-aggregated REDs, after the shared-memory count has
+// written / added its slices.  Keys of buckets [bucket_lo, bucket_hi) only; buckets counted by k_count_keys are skipped.
+__global__ void __launch_bounds__(256)
+k_count_spill(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta, L2Layout Y, int bucket_lo, int bucket_hi,
+              uint32_t* __restrict__ table) {
+    if (meta->overflow) return;
+    const uint64_t n = min(meta->spill_n, (ull)Y.spill_cap);
+    const uint32_t* __restrict__ spill = reinterpret_cast<const uint32_t*>(ws + Y.spill0);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)); i0 < n; i0 += stride) {
+        const uint64_t i = i0 + (threadIdx.x & 31u);
+        bool act = i < n;
+        uint32_t key = 0;
+        if (act) {
+            key = __ldcs(spill + i);
+            const int b = (int)((key - Y.key_lo) >> Y.shift);
+            act = b >= bucket_lo && b < bucket_hi && !meta->overflow2[b];
+        }
+        red_aggregated(table, key, act);
+    }
 }
 
 // one CTA per sub-slice: its segments -> 2^15 counters in shared memory -> added to the table slice (128 KB, contiguous)
@@ -898,7 +1019,8 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
     // second-level lists (shared-memory count): built chunk by chunk in add() when the workspace has room for them
     part->l2_enabled = 0;
     part->l2_ncta = part->l2_C3 = 0;
-    part->l2_seg0 = part->l2_span = 0;
+    part->l2_seg0 = part->l2_span = part->l2_spill0 = 0;
+    part->l2_spill_cap = 0;
     const int sub_bits = shift - 16;
     if (part->sub && sub_bits >= 0) {
         const uint64_t nsub = 1ull << sub_bits;
@@ -906,7 +1028,12 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
         const uint64_t n_cta = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * kL2CtasPerSm, 1024), part->capacity / ((uint64_t)kStepSlots * nb)));
         const uint64_t seg0 = (n_cta * nb * nsub * 2 + 7) & ~7ull;               // fill counters (u32) in u16 units
         const uint64_t segs = (uint64_t)nb * nsub * n_cta;
-        uint64_t C3 = part->sub_capacity > seg0 + (uint64_t)nb * kStepSlots ? ((part->sub_capacity - seg0 - (uint64_t)nb * kStepSlots) / segs) & ~7ull : 0;
+        // spill area (u32 keys) at the end of the workspace: 1/8 of the list capacity, i.e. 1/8 of ALL windows may sit in
+        // rows or segments that overflowed before any bucket has to fall back to k_count_keys
+        const uint64_t spill_cap = std::min<uint64_t>(std::max<uint64_t>(part->capacity / 8, 1u << 16), 0xFFFFFFF0ull);
+        const uint64_t spill_u16 = 2 * spill_cap + 8;
+        const uint64_t usable = part->sub_capacity > spill_u16 ? (part->sub_capacity - spill_u16) & ~7ull : 0;
+        uint64_t C3 = usable > seg0 + (uint64_t)nb * kStepSlots ? ((usable - seg0 - (uint64_t)nb * kStepSlots) / segs) & ~7ull : 0;
         if (nsub * n_cta * C3 + kStepSlots >= (1ull << 32)) C3 = ((((1ull << 32) - 8 - kStepSlots) / (nsub * n_cta))) & ~7ull;
         // worth building only if the segments could hold every window with some slack (else most buckets would fall back)
         if (C3 >= 8 && segs * C3 >= part->capacity + part->capacity / 4) {
@@ -915,6 +1042,8 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
             part->l2_C3 = (uint32_t)C3;
             part->l2_seg0 = seg0;
             part->l2_span = nsub * n_cta * C3 + kStepSlots;
+            part->l2_spill0 = usable;
+            part->l2_spill_cap = (uint32_t)spill_cap;
             LRB_CUDA(cudaMemsetAsync(part->sub, 0, seg0 * sizeof(uint16_t), (cudaStream_t)stream));
         }
     }
@@ -962,6 +1091,7 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
         L2Layout Y;
         Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
         Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
+        Y.spill0 = part->l2_spill0; Y.spill_cap = part->l2_spill_cap; Y.key_lo = part->key_lo; Y.shift = shift;
         constexpr int kSmemL2 = kL2Stage * (int)sizeof(uint16_t);
 #define LRB_LAUNCH_K2(LG)                                                                                               \
     case LG:                                                                                                            \
@@ -1037,10 +1167,11 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     // second-level (shared-memory) counting needs the sub-slice lists built by add(); without them the L2-atomic kernel does the job
     const bool smem_count = do_count && (mode & 4) && part->l2_enabled;
     const bool overwrite = do_count && (mode & 8);   // the caller did not zero the slices of the applied buckets
-    L2Layout Y = {0, 0, 0, 0, 0, 0, 0, 0};
+    L2Layout Y = {};
     if (smem_count) {
         Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
         Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
+        Y.spill0 = part->l2_spill0; Y.spill_cap = part->l2_spill_cap; Y.key_lo = part->key_lo; Y.shift = part->shift;
     }
     if (do_search) {
         if (!hist || !sums) return lrb_set_error(LRB_EINVAL, "lrb_dev_partition_apply: search needs hist and sums");
@@ -1088,6 +1219,7 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
         if (overwrite) LRB_LAUNCH("k_count_smem", st, k_count_smem<true><<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table));
         else LRB_LAUNCH("k_count_smem", st, k_count_smem<false><<<g1, 1024, kSmemTable, st>>>(part->sub, meta, bucket_lo, Y, base0, shift, table));
         LRB_LAUNCH("k_count_keys", st, k_count_keys<<<g2, 256, 0, st>>>(part->keys, meta, bucket_lo, part->n_chunks, base0, shift, hi_mask2, table, 1));
+        LRB_LAUNCH("k_count_spill", st, k_count_spill<<<grid, 256, 0, st>>>(part->sub, meta, Y, bucket_lo, bucket_hi, table));
     }
     const bool search_batched = do_search && !do_count && bucket_hi > bucket_lo;
     if (search_batched) {
@@ -1107,6 +1239,7 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
         if (smem_count && overwrite) LRB_LAUNCH("k_count_smem", st, k_count_smem<true><<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table));
         else if (smem_count) LRB_LAUNCH("k_count_smem", st, k_count_smem<false><<<Y.nsub, 1024, kSmemTable, st>>>(part->sub, meta, b, Y, bucket_base, shift, table));
         if (do_count) LRB_LAUNCH("k_count_keys", st, k_count_keys<<<grid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, bucket_base, shift, hi_mask2, table, smem_count ? 1 : 0));
+        if (smem_count) LRB_LAUNCH("k_count_spill", st, k_count_spill<<<grid, 256, 0, st>>>(part->sub, meta, Y, b, b + 1, table));
         if (do_search) {
 #define LRB_LAUNCH_SEARCH(LUT, UN, ...)                                                                                                \
     LRB_LAUNCH("k_search_keys", st, k_search_keys<LUT, UN, ##__VA_ARGS__><<<sgrid, 256, 0, st>>>(part->keys, meta, b, part->n_chunks, L, T, bucket_base, hi_mask2, shift, table, S32, magic, \

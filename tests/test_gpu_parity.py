@@ -522,7 +522,7 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     assert torch.equal(table_p, table_m)
     # barely enough room for the second-level lists: many (bucket, sub-slice, CTA) segments overflow and their buckets fall
     # back to the L2-atomic kernel, the others go through shared memory — one table
-    tiny = PartitionWorkspace(dr, sub_capacity=int(1.3 * ws.capacity) + (1 << 20))
+    tiny = PartitionWorkspace(dr, sub_capacity=int(1.6 * ws.capacity) + (1 << 20))
     table_p = torch.full((2 ** 30,), 7, dtype=torch.int32, device=DEV)
     dev_table15_partitioned(dr, tiny, table_p, True)
     dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=25)
@@ -553,10 +553,21 @@ def test_partitioned_l2_resident_passes_equal_direct_kernels():
     assert torch.equal(table_p, table_d) and torch.equal(hist_p, hist_d) and torch.equal(sums_p, sums_d)
 
 
+_META_O2 = 2 * 64 * 64 + 65 + 2      # PartMeta (csrc/partition.cu) in u64 units: counts, offsets [64][64], chunk_base[65], needed, overflow,
+                                     # then overflow2 u32[64] (32 u64), spill_n, spill_dropped
+
+
+def _part_meta(ws):
+    m = ws.small.cpu().numpy()
+    o2 = m[_META_O2:_META_O2 + 32].view(np.uint32)[:ws.part.n_buckets].astype(bool)
+    return int(o2.sum()), int(m[_META_O2 + 32]), int(m[_META_O2 + 33])   # buckets fallen back, spilled entries, spill area overflowed
+
+
 def test_second_level_count_survives_key_skew():
     """Low-complexity reads (tandem repeats, homopolymers) pile thousands of windows of one 8192-entry tile into a single
-    2^15-key sub-slice: k2_partition's fixed staging rows overflow into its per-tile overflow list, and where that (or a
-    list segment) overflows too the bucket falls back to k_count_keys.  Whatever the mix of paths, one table."""
+    2^15-key sub-slice: k2_partition's fixed staging rows overflow into its per-tile overflow list, beyond that (or when a
+    list segment is full) the entries go to the spill area and are applied by k_count_spill; only when the spill area
+    fills up does a bucket fall back to k_count_keys.  Whatever the mix of paths, one table."""
     rng = np.random.default_rng(77)
     spec = SynthSpec(2500, seed=31, scale=0.05)
     seqs = spec.host_sequences()
@@ -573,7 +584,7 @@ def test_second_level_count_survives_key_skew():
     dev_count(dr, table_d)
     # roomy list segments, so that a repeat read's ~1000 windows of one key overflow only the per-tile staging row
     ws = PartitionWorkspace(dr, sub_capacity=40 * pr.n_blocks * 32)
-    fell_back = {}
+    fell_back, spilled = {}, {}
     for shift in (24, 25, 22):
         table_p = z(2 ** 30)
         if shift == 22:                                    # 64 buckets of 2^22 keys cover a quarter of the key space at a time
@@ -581,9 +592,8 @@ def test_second_level_count_survives_key_skew():
                 dev_table15_partitioned(dr, ws, table_p, True, key_lo=q * 2 ** 28, key_hi=(q + 1) * 2 ** 28, log2_bucket_keys=22)
         else:
             dev_table15_partitioned(dr, ws, table_p, True, log2_bucket_keys=shift)
-            # PartMeta.overflow2 (csrc/partition.cu): counts, offsets [64][64] u64, chunk_base[65], needed, overflow, then u32[64]
-            o2 = ws.small[2 * 64 * 64 + 65 + 2:2 * 64 * 64 + 65 + 2 + 32].cpu().numpy().view(np.uint32)
-            fell_back[shift] = int(o2[:ws.part.n_buckets].astype(bool).sum())
+            fell_back[shift], spilled[shift], dropped = _part_meta(ws)
+            assert not dropped
         assert torch.equal(table_p, table_d), shift
         if shift != 22:                                    # the same mix of paths, writing instead of adding
             table_w = torch.full((2 ** 30,), 123456789, dtype=torch.int32, device=DEV)
@@ -591,8 +601,26 @@ def test_second_level_count_survives_key_skew():
             ws.apply(table_w, count=True, overwrite=True)
             assert torch.equal(table_w.view(-1, 2, 1 << 15)[:, 0, :], table_d.view(-1, 2, 1 << 15)[:, 0, :]), shift
             del table_w
-    # the homopolymer bucket must have fallen back; most buckets must not have (they took the overflow-list path at worst)
-    assert 1 <= fell_back[24] <= 32, fell_back
+    # the homopolymers (290 000 windows of one key) cannot fit any list segment: they went through the spill area, and no
+    # bucket had to fall back
+    assert fell_back[24] == 0 and fell_back[25] == 0, fell_back
+    assert spilled[24] > 200000 and spilled[25] > 200000, spilled
+    # a read set DOMINATED by one key overflows the spill area (1/8 of the list capacity): its bucket falls back to the
+    # (aggregating) L2-atomic kernel, the other buckets still go through shared memory; adding and writing forms
+    seqs2 = seqs[:600] + [b"A" * 6000] * 400
+    pr2 = PackedReads.from_sequences(seqs2)
+    dr2 = DeviceReads(pr2, DEV)
+    table_d2 = z(2 ** 30)
+    dev_count(dr2, table_d2)
+    ws2 = PartitionWorkspace(dr2)
+    table_p = z(2 ** 30)
+    dev_table15_partitioned(dr2, ws2, table_p, True)
+    fb, sp, dropped = _part_meta(ws2)
+    assert dropped and 1 <= fb <= 4 and torch.equal(table_p, table_d2), (fb, sp, dropped)
+    table_w = torch.full((2 ** 30,), 987654321, dtype=torch.int32, device=DEV)
+    ws2.build(True)
+    ws2.apply(table_w, count=True, overwrite=True)
+    assert torch.equal(table_w.view(-1, 2, 1 << 15)[:, 0, :], table_d2.view(-1, 2, 1 << 15)[:, 0, :])
 
 
 def test_multi_gpu_exchange_building_blocks_on_one_device():

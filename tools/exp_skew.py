@@ -67,12 +67,14 @@ for frac in [float(x) for x in a.fractions.split(",")]:
     _lib.lib.lrb_prof_enable(0)
     prof = _lib.prof_report()
     ms = t0.elapsed_time(t1) / a.steps
-    # PartMeta.overflow2 (csrc/partition.cu): counts, offsets [64][64] u64, chunk_base[65], needed, overflow, then u32[64]
-    o2 = ws.small[2 * 64 * 64 + 65 + 2:2 * 64 * 64 + 65 + 2 + 32].cpu().numpy().view(np.uint32)
+    # PartMeta (csrc/partition.cu) in u64 units: counts, offsets [64][64], chunk_base[65], needed, overflow, overflow2 u32[64], spill_n
+    meta = ws.small.cpu().numpy()
+    o2 = meta[2 * 64 * 64 + 65 + 2:2 * 64 * 64 + 65 + 2 + 32].view(np.uint32)
+    spill_n = int(meta[2 * 64 * 64 + 65 + 2 + 32])
     V = int(sums.to(torch.int64).sum().item())
     assert int(hist.to(torch.int64).sum().item()) == V
     print(json.dumps({"low_complexity_fraction": frac, "reads": n, "bases": Lb, "valid_windows": V, "ms_per_step": ms,
-                      "Gbases_per_s": Lb / ms / 1e6, "buckets_counted_by_L2_atomics": int(o2[:ws.part.n_buckets].astype(bool).sum()),
+                      "Gbases_per_s": Lb / ms / 1e6, "buckets_counted_by_L2_atomics": int(o2[:ws.part.n_buckets].astype(bool).sum()), "entries_through_the_spill_area": spill_n,
                       "kernel_ms_per_step": {kk: round(v[1] / a.steps, 3) for kk, v in prof.items() if v[1] / a.steps >= 0.01}}), flush=True)
     del ws, table, comp, hist, sums, dr, pr
     torch.cuda.empty_cache()
