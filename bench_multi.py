@@ -424,7 +424,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
             line["north_star"].append({
                 "workload": name, "scaling": "strong", "reads": S2.n, "bases": S2.L, "k": c2["k"], "n_gpus": world,
                 "plan": b2, "plan_ms": pm, "ms_per_step": pm[b2], "value": S2.L / pm[b2] / 1e6, "unit": "Gbases/s",
-                "phases_ms_rank0": ph[b2], "verify": v2,
+                "phases_ms_rank0": ph[b2], "plan_phases_ms_rank0": ph, "verify": v2,
                 "load_imbalance_max_over_mean_slots": float(mx.item()) / (float(own_bases.item()) / world)})
             S2.close()
             del S2, r2

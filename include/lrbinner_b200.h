@@ -274,6 +274,8 @@ typedef struct {
     float wall_ms;            /* host wall clock of the call */
     float exchange_ms;        /* device 0: first to last operation of the table exchange (0 on one GPU) */
     uint64_t batch_bases_max; /* slots of the largest batch */
+    float host_plan_ms;       /* host: entry -> devices, tables and batches planned */
+    float host_enqueue_ms;    /* host: entry -> device 0's last operation enqueued (the rest of wall_ms is waiting for the device) */
 } lrb_run_info;
 int lrb_ctx_last_info(const lrb_ctx* ctx, lrb_run_info* info);
 /* Device milliseconds (CUDA events) of the last lrb_profile_host call.  The call is a 3-stream pipeline, so the

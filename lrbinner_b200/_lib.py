@@ -45,7 +45,8 @@ PART_SMALL_U64 = 16384
 class RunInfo(C.Structure):
     """lrb_run_info: how the last lrb_profile_host call ran."""
     _fields_ = [("n_devices", C.c_int), ("n_batches", C.c_int), ("table_path", C.c_int), ("lists_reused", C.c_int),
-                ("wall_ms", C.c_float), ("exchange_ms", C.c_float), ("batch_bases_max", C.c_uint64)]
+                ("wall_ms", C.c_float), ("exchange_ms", C.c_float), ("batch_bases_max", C.c_uint64),
+                ("host_plan_ms", C.c_float), ("host_enqueue_ms", C.c_float)]
 
 
 PROFILE_USE_LOADED_TABLE, PROFILE_KEEP_TABLE = 1, 2

@@ -719,6 +719,9 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
                 streamed ? " (working set larger than device memory: reads are shipped and partitioned once per pass)" : "",
                 J.use_part ? "key-partitioned, L2-resident" : "direct (LRB_TABLE_PATH=direct)");
 
+    auto since0 = [&]() { return (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count(); };
+    info.host_plan_ms = since0();
+
     // ---- pass 1 -----------------------------------------------------------------------------------------------------
     c->table_ready = J.use_loaded ? c->table_ready : false;
     if (J.use_loaded && multi) {   // the loaded table lives on device 0: hand it to the others
@@ -851,6 +854,7 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         if (x == c && table_host)
             CTX_CUDA(cudaMemcpyAsync(table_host, c->table.p, sizeof(uint32_t) * (size_t)kTableEntries, cudaMemcpyDeviceToHost, st));
         if (x == c) CTX_CUDA(cudaEventRecord(c->ev[6], st));
+        if (x == c) info.host_enqueue_ms = since0();   // everything is enqueued (single batch); what follows is waiting for the device
         return sync_ctx(x);
     });
     cleanup();
