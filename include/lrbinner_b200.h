@@ -181,6 +181,7 @@ typedef struct {
     int l2_enabled;                /* second-level lists are being built (filled by begin()) */
     uint32_t l2_ncta, l2_C3;
     uint64_t l2_seg0, l2_span;
+    uint64_t l2_cells0;            /* per-(bucket, sub-slice) segment table (offsets, capacities, sampled histogram), u16 offset in `sub` */
     uint64_t l2_spill0;            /* spill area of the second level (hot keys), u16 offset in `sub` */
     uint32_t l2_spill_cap;         /* ... and its capacity in entries */
 } lrb_partition;

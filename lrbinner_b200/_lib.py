@@ -36,7 +36,7 @@ class Partition(C.Structure):
                 ("key_lo", C.c_uint32), ("key_hi", C.c_uint32),
                 ("chunk_step0", C.c_uint32 * 64), ("chunk_nsteps", C.c_uint32 * 64),
                 ("l2_enabled", C.c_int), ("l2_ncta", C.c_uint32), ("l2_C3", C.c_uint32), ("l2_seg0", C.c_uint64), ("l2_span", C.c_uint64),
-                ("l2_spill0", C.c_uint64), ("l2_spill_cap", C.c_uint32)]
+                ("l2_cells0", C.c_uint64), ("l2_spill0", C.c_uint64), ("l2_spill_cap", C.c_uint32)]
 
 
 PART_SMALL_U64 = 16384

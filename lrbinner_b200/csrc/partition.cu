@@ -432,15 +432,23 @@ constexpr uint32_t kL2Run = 8;    // consecutive tiles of one bucket a CTA takes
 constexpr int kL2CtasPerSm = 2;   // measured: a third CTA per SM (fits: 40 registers, 74 KB) makes the kernel 40 % slower (l1tex is already 80 % busy)
 
 struct L2Layout {
-    uint32_t nsub, n_cta, C3, nb;   // sub-slices per bucket, CTAs of k2_partition, entries per segment, buckets
-    uint32_t cta_major;             // segment order inside a bucket: [cta][sub] (1) or [sub][cta] (0)
+    uint32_t nsub, n_cta, C3, nb;   // sub-slices per bucket, CTAs of k2_partition, UNIFORM entries per segment (small inputs), buckets
     uint32_t strided;               // k2_partition row ownership (fill rows are permuted to match)
-    __host__ __device__ uint32_t seg(uint32_t sub, uint32_t cta) const { return cta_major ? cta * nsub + sub : sub * n_cta + cta; }
     // position of a sub-slice's counter in a fill row: the sub-slices warp + 16 j that one k2_partition warp owns sit next to
     // each other, so its lanes read and write one 64-byte stretch instead of 16 sectors
     __host__ __device__ uint32_t fill_pos(uint32_t sub) const { return (sub & 15u) * (nsub >> 4) + (sub >> 4); }
-    uint64_t seg0, span;            // first segment; u16 units per bucket (its segments + a spare tile)
-    __host__ __device__ uint64_t bucket_base(uint32_t b) const { return seg0 + (uint64_t)b * span; }
+    // Segments.  A CELL is one (bucket, sub-slice) pair, cell = bucket * nsub + sub; its n_cta segments of cell_cap[cell]
+    // entries each lie back to back ([cta][cap]) at seg0 + 8 * cell_off[cell] (u16 units; offsets are kept in octets so
+    // that 32 bits reach 64 GB).  Capacities FOLLOW THE KEY DISTRIBUTION: k_sample_cells histograms the cells of a
+    // sample of the first chunk's blocks, k_plan_cells hands every cell its share of the segment space (plus a floor), so a
+    // GC-skewed community fills its segments as evenly as a uniform one (round 1 / early round 2 gave every cell the same
+    // capacity and leaned on the fallback / spill area).  Too small a sample -> the uniform C3.
+    uint64_t seg0, seg_units;       // first segment; u16 units available for segments
+    uint64_t cells0;                // u16 offset of the cell table: u32 cell_off[ncell + 1], u32 cell_cap[ncell], u32 cell_hist[ncell]
+    __host__ __device__ uint32_t ncell() const { return nb * nsub; }
+    __device__ const uint32_t* cell_off(const uint16_t* ws) const { return reinterpret_cast<const uint32_t*>(ws + cells0); }
+    __device__ const uint32_t* cell_cap(const uint16_t* ws) const { return cell_off(ws) + ncell() + 1; }
+    __device__ uint32_t* cell_hist(uint16_t* ws) const { return reinterpret_cast<uint32_t*>(ws + cells0) + 2 * ncell() + 1; }
     // spill area: full table keys (u32) of the entries that found their staging row, the tile's overflow list or their
     // segment full (hot keys: low-complexity reads put thousands of equal windows into one tile); applied with warp-
     // aggregated REDs by k_count_spill after the shared-memory count
@@ -452,6 +460,71 @@ struct L2Layout {
         return key_lo + (bucket << shift) + (sub << 16) + low15;
     }
 };
+
+constexpr uint32_t kCellFloor = 16;   // entries every segment gets whatever the sample says
+
+// cells of a sample of the chunk's blocks (every `stride`-th block, one thread per sampled block)
+template <bool FULL>
+__global__ void __launch_bounds__(256)
+k_sample_cells(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ valid, uint64_t blk_lo, uint64_t blk_hi, uint64_t stride,
+               uint32_t key_lo, uint32_t key_hi, uint16_t* __restrict__ ws, L2Layout Y) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gb = blk_lo + i * stride;
+    BlockWindows b;
+    b.m = b.pw = b.w0 = b.w1 = 0;
+    if (gb < blk_hi) b = load_block(codes, valid, gb);
+    uint32_t* __restrict__ hist = Y.cell_hist(ws);
+    for_each_key<FULL>(b, key_lo, key_hi, [&](uint32_t kk) { atomicAdd(hist + ((kk - key_lo) >> 16), 1u); });
+}
+
+// one CTA: capacities and offsets of all cells from the sampled histogram
+__global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, L2Layout Y) {
+    __shared__ ull s_red[1024];
+    __shared__ ull s_scan[1024];
+    const uint32_t tid = threadIdx.x, ncell = Y.ncell();
+    uint32_t* off = const_cast<uint32_t*>(Y.cell_off(ws));
+    uint32_t* cap = const_cast<uint32_t*>(Y.cell_cap(ws));
+    const uint32_t* hist = Y.cell_hist(ws);
+    ull sum = 0;
+    for (uint32_t c = tid; c < ncell; c += 1024) sum += hist[c];
+    s_red[tid] = sum;
+    __syncthreads();
+    for (int d = 512; d > 0; d >>= 1) {
+        if (tid < (uint32_t)d) s_red[tid] += s_red[tid + d];
+        __syncthreads();
+    }
+    const ull total = s_red[0];
+    // per-CTA entries to hand out beyond the floor; a bucket's segments must stay below 2^32 u16 units (32-bit row offsets)
+    const ull per_cta = Y.seg_units / Y.n_cta;
+    const ull floor_all = (ull)ncell * kCellFloor;
+    const bool uniform = total < 32ull * ncell || per_cta <= floor_all;
+    const ull avail = uniform ? 0ull : per_cta - floor_all;
+    const ull clamp = ((1ull << 32) - 8 - kStepSlots) / ((ull)Y.nsub * Y.n_cta);
+    // contiguous stretch of cells per thread, so that one scan over the threads' totals gives every cell its offset
+    const uint32_t per = (ncell + 1023u) / 1024u;
+    const uint32_t c0 = min(ncell, tid * per), c1 = min(ncell, c0 + per);
+    ull mine = 0;
+    for (uint32_t c = c0; c < c1; ++c) {
+        ull w = uniform ? (ull)Y.C3 : kCellFloor + (ull)hist[c] * avail / total;
+        w = min(w, clamp) & ~7ull;
+        cap[c] = (uint32_t)w;
+        mine += w * Y.n_cta / 8;   // octets
+    }
+    s_scan[tid] = mine;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const ull v = tid >= (uint32_t)d ? s_scan[tid - d] : 0ull;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    ull acc = s_scan[tid] - mine;
+    for (uint32_t c = c0; c < c1; ++c) {
+        off[c] = (uint32_t)acc;
+        acc += (ull)cap[c] * Y.n_cta / 8;
+    }
+    if (tid == 1023) off[ncell] = (uint32_t)s_scan[1023];
+}
 
 template <int LOG2_NSUB, bool STRIDED>
 __global__ void __launch_bounds__(kL2Threads, kL2CtasPerSm)
@@ -541,6 +614,8 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     };
     const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
     uint32_t* __restrict__ spill_keys = reinterpret_cast<uint32_t*>(ws + Y.spill0);
+    const uint32_t* __restrict__ c_off = Y.cell_off(ws);
+    const uint32_t* __restrict__ c_cap = Y.cell_cap(ws);
     // n keys of this warp into the spill area: one reservation per call (warp-aggregated), keys produced by key_at(i).
     // When the area is full the remaining keys are dropped and the bucket is flagged: k_count_keys then counts the whole
     // bucket from the first-level list and both other count kernels skip it.
@@ -567,6 +642,11 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         const uint32_t par = it & 1u;
         uint32_t* frow = fill + (size_t)b_cur * nsub;
         const uint32_t f_my = lane < spw ? frow[my_pos] : 0u;    // written only by this lane (previous tiles of this CTA)
+        // this row's segment: capacity and position relative to the bucket's first segment
+        const uint32_t cell0 = b_cur * nsub;
+        const uint32_t cap_my = lane < spw ? __ldg(c_cap + cell0 + my_sub) : 0u;
+        const uint32_t boff0 = __ldg(c_off + cell0);
+        const uint32_t rel_my = lane < spw ? (__ldg(c_off + cell0 + my_sub) - boff0) * 8u + blockIdx.x * cap_my : 0u;
         // place: one returning atomic + one predicated 2-byte store per entry (the staged half-word keeps entry bit 15, a
         // sub-slice bit: k_count_smem masks it off); entries that find their row full are remembered in a bit mask and go
         // to the overflow list afterwards
@@ -634,14 +714,14 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
             const uint32_t gone = s_sp2[my_sub];
             if (gone) { n_my -= gone; s_sp2[my_sub] = 0; }
         }
-        const bool ok_my = f_my + n_my <= Y.C3;   // a full segment takes nothing more (its bucket falls back)
+        const bool ok_my = f_my + n_my <= cap_my;   // a full segment takes nothing more: the row goes to the spill area
         uint32_t ns_my = 0, off_my = 0;
         if (lane < spw && n_my) {
             s_cnt[my_sub] = 0;
             if (ok_my) {
                 frow[my_pos] = f_my + n_my;
                 ns_my = min(n_my, cap);
-                off_my = Y.seg(my_sub, blockIdx.x) * Y.C3 + f_my;   // < 2^32 (lrb_dev_partition_begin clamps C3)
+                off_my = rel_my + f_my;   // < 2^32 (k_plan_cells clamps the capacities)
             }
         }
         if (tid == 0) s_novl[par ^ 1u] = 0;  // the next tile's list; last read before the previous tile's closing barrier
@@ -672,7 +752,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
                 }
             }
         }
-        uint16_t* __restrict__ lists = ws + Y.bucket_base(b_cur);
+        uint16_t* __restrict__ lists = ws + Y.seg0 + 8ull * boff0;
         constexpr uint32_t cm = cap - 1u;
         const uint32_t big = __ballot_sync(0xFFFFFFFFu, ns_my > 64u || (ok_my && n_my > cap));  // rows the fast loop does not finish
 #pragma unroll
@@ -757,7 +837,9 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     }
     const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + (Y.strided ? Y.fill_pos(sub) : sub);  // + cta * nb * nsub
     const size_t fill_stride = (size_t)Y.nb * Y.nsub;
-    const uint16_t* __restrict__ lists = ws + Y.bucket_base(bucket);
+    const uint32_t cell = (uint32_t)bucket * Y.nsub + sub;
+    const uint32_t seg_cap = __ldg(Y.cell_cap(ws) + cell);
+    const uint16_t* __restrict__ lists = ws + Y.seg0 + 8ull * __ldg(Y.cell_off(ws) + cell);   // this cell's n_cta segments
     uint4* tab4 = reinterpret_cast<uint4*>(s_tab);
     for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) tab4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -773,7 +855,7 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     const uint32_t my_len = my_cta < Y.n_cta ? __ldg(fill + my_cta * fill_stride) : 0u;
     const uint32_t n_seg = (Y.n_cta > warp) ? (Y.n_cta - warp + 31u) / 32u : 0u;   // segments of this warp (n_cta <= 1024)
     bool any = __any_sync(0xFFFFFFFFu, my_len != 0u);
-    auto seg_ptr = [&](uint32_t k) { return lists + (size_t)Y.seg(sub, warp + 32u * k) * Y.C3; };
+    auto seg_ptr = [&](uint32_t k) { return lists + (size_t)(warp + 32u * k) * seg_cap; };
     auto fetch4 = [&](uint32_t k, uint32_t n, uint4* v) {
         const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(seg_ptr(k));
         const uint32_t n8 = n / 8;
@@ -958,11 +1040,6 @@ __global__ void __launch_bounds__(256) k_row_sums(const uint32_t* __restrict__ h
     sums[r] = s;
 }
 
-uint32_t l2_cta_major() {  // experiment switch (LRB_K2_LAYOUT=cta): segments of one k2_partition CTA next to each other
-    const char* e = getenv("LRB_K2_LAYOUT");
-    return (e && e[0] == 'c') ? 1u : 0u;
-}
-
 uint32_t l2_strided() {  // which rows a k2_partition warp sweeps: "strided" (warp + 16 j, default: 2 ms faster) or "block" (16 warp + j)
     const char* e = getenv("LRB_K2_ROWS");
     return (e && e[0] == 'b') ? 0u : 1u;
@@ -1019,32 +1096,39 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
     // second-level lists (shared-memory count): built chunk by chunk in add() when the workspace has room for them
     part->l2_enabled = 0;
     part->l2_ncta = part->l2_C3 = 0;
-    part->l2_seg0 = part->l2_span = part->l2_spill0 = 0;
+    part->l2_seg0 = part->l2_span = part->l2_spill0 = part->l2_cells0 = 0;
     part->l2_spill_cap = 0;
     const int sub_bits = shift - 16;
     if (part->sub && sub_bits >= 0) {
         const uint64_t nsub = 1ull << sub_bits;
         // CTAs of k2_partition: kL2CtasPerSm per SM, fewer when the lists cannot have that many tiles anyway (small inputs keep big segments)
         const uint64_t n_cta = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>((uint64_t)sms() * kL2CtasPerSm, 1024), part->capacity / ((uint64_t)kStepSlots * nb)));
-        const uint64_t seg0 = (n_cta * nb * nsub * 2 + 7) & ~7ull;               // fill counters (u32) in u16 units
-        const uint64_t segs = (uint64_t)nb * nsub * n_cta;
+        // workspace (u16 units): fill counters | cell table | segments ... spare tile | spill area
+        const uint64_t ncell = (uint64_t)nb * nsub;
+        const uint64_t fill_u16 = (n_cta * ncell * 2 + 7) & ~7ull;               // fill counters (u32)
+        const uint64_t cells_u16 = ((3 * ncell + 1) * 2 + 7) & ~7ull;            // cell_off[ncell+1], cell_cap[ncell], cell_hist[ncell] (u32)
+        const uint64_t seg0 = fill_u16 + cells_u16;
+        const uint64_t segs = ncell * n_cta;
         // spill area (u32 keys) at the end of the workspace: 1/8 of the list capacity, i.e. 1/8 of ALL windows may sit in
         // rows or segments that overflowed before any bucket has to fall back to k_count_keys
         const uint64_t spill_cap = std::min<uint64_t>(std::max<uint64_t>(part->capacity / 8, 1u << 16), 0xFFFFFFF0ull);
         const uint64_t spill_u16 = 2 * spill_cap + 8;
         const uint64_t usable = part->sub_capacity > spill_u16 ? (part->sub_capacity - spill_u16) & ~7ull : 0;
-        uint64_t C3 = usable > seg0 + (uint64_t)nb * kStepSlots ? ((usable - seg0 - (uint64_t)nb * kStepSlots) / segs) & ~7ull : 0;
+        const uint64_t seg_units = usable > seg0 + kStepSlots ? (usable - seg0 - kStepSlots) & ~7ull : 0;   // a spare tile stays behind the last segment
+        uint64_t C3 = (seg_units / segs) & ~7ull;                                // uniform capacity (small inputs, too small a sample)
         if (nsub * n_cta * C3 + kStepSlots >= (1ull << 32)) C3 = ((((1ull << 32) - 8 - kStepSlots) / (nsub * n_cta))) & ~7ull;
-        // worth building only if the segments could hold every window with some slack (else most buckets would fall back)
-        if (C3 >= 8 && segs * C3 >= part->capacity + part->capacity / 4) {
+        // worth building only if the segments could hold every window with some slack (else most rows would spill);
+        // cell offsets are 32-bit counts of octets: 64 GB of segments at most
+        if (C3 >= 8 && segs * C3 >= part->capacity + part->capacity / 4 && seg_units / 8 < (1ull << 32)) {
             part->l2_enabled = 1;
             part->l2_ncta = (uint32_t)n_cta;
             part->l2_C3 = (uint32_t)C3;
+            part->l2_cells0 = fill_u16;
             part->l2_seg0 = seg0;
-            part->l2_span = nsub * n_cta * C3 + kStepSlots;
+            part->l2_span = seg_units;
             part->l2_spill0 = usable;
             part->l2_spill_cap = (uint32_t)spill_cap;
-            LRB_CUDA(cudaMemsetAsync(part->sub, 0, seg0 * sizeof(uint16_t), (cudaStream_t)stream));
+            LRB_CUDA(cudaMemsetAsync(part->sub, 0, seg0 * sizeof(uint16_t), (cudaStream_t)stream));   // fill counters and cell histogram
         }
     }
     return LRB_OK;
@@ -1089,9 +1173,18 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
 #undef LRB_LAUNCH_PART
     if (part->l2_enabled) {
         L2Layout Y;
-        Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
-        Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
+        Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb; Y.strided = l2_strided();
+        Y.seg0 = part->l2_seg0; Y.seg_units = part->l2_span; Y.cells0 = part->l2_cells0;
         Y.spill0 = part->l2_spill0; Y.spill_cap = part->l2_spill_cap; Y.key_lo = part->key_lo; Y.shift = shift;
+        if (c == 0) {   // segment capacities from the key distribution of a sample of the first chunk (see L2Layout)
+            const uint64_t stride = std::max<uint64_t>(1, nblk >> 21);
+            const uint64_t n_samp = (nblk + stride - 1) / stride;
+            if (full)
+                LRB_LAUNCH("k_sample_cells", st, k_sample_cells<true><<<(unsigned)((n_samp + 255) / 256), 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, stride, part->key_lo, part->key_hi, part->sub, Y));
+            else
+                LRB_LAUNCH("k_sample_cells", st, k_sample_cells<false><<<(unsigned)((n_samp + 255) / 256), 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, stride, part->key_lo, part->key_hi, part->sub, Y));
+            LRB_LAUNCH("k_plan_cells", st, k_plan_cells<<<1, 1024, 0, st>>>(part->sub, Y));
+        }
         constexpr int kSmemL2 = kL2Stage * (int)sizeof(uint16_t);
 #define LRB_LAUNCH_K2(LG)                                                                                               \
     case LG:                                                                                                            \
@@ -1169,8 +1262,8 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     const bool overwrite = do_count && (mode & 8);   // the caller did not zero the slices of the applied buckets
     L2Layout Y = {};
     if (smem_count) {
-        Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets; Y.cta_major = l2_cta_major(); Y.strided = l2_strided();
-        Y.seg0 = part->l2_seg0; Y.span = part->l2_span;
+        Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets; Y.strided = l2_strided();
+        Y.seg0 = part->l2_seg0; Y.seg_units = part->l2_span; Y.cells0 = part->l2_cells0;
         Y.spill0 = part->l2_spill0; Y.spill_cap = part->l2_spill_cap; Y.key_lo = part->key_lo; Y.shift = part->shift;
     }
     if (do_search) {

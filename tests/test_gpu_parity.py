@@ -625,6 +625,41 @@ def test_second_level_count_survives_key_skew():
     assert torch.equal(table_w.view(-1, 2, 1 << 15)[:, 0, :], table_d2.view(-1, 2, 1 << 15)[:, 0, :])
 
 
+def test_segment_capacities_follow_the_key_distribution():
+    """An AT-rich genome (20 % GC) puts ~6x the mean into the AT-rich (bucket, sub-slice) cells and next to nothing into
+    the GC-rich ones.  k_sample_cells / k_plan_cells size the second-level segments from a sample of the windows, so the
+    whole set still goes through the shared-memory count: no bucket falls back, only a sliver passes the spill area."""
+    rng = np.random.default_rng(5)
+    genome = rng.choice(np.frombuffer(b"ACTG", dtype=np.uint8), size=8_000_000, p=[0.4, 0.1, 0.4, 0.1])
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    seqs = []
+    for _ in range(40000):
+        L = int(rng.integers(2000, 8000))
+        st = int(rng.integers(0, len(genome) - L))
+        r = genome[st:st + L]
+        seqs.append((comp[r[::-1]] if rng.random() < 0.5 else r).tobytes())
+    pr = PackedReads.from_sequences(seqs, threads=8)
+    dr = DeviceReads(pr, DEV)
+    table_d = torch.zeros(2 ** 30, dtype=torch.int32, device=DEV)
+    dev_count(dr, table_d)
+    ws = PartitionWorkspace(dr)
+    for shift in (24, 25):
+        table_p = torch.full((2 ** 30,), 31337, dtype=torch.int32, device=DEV)
+        ws.build(True, log2_bucket_keys=shift)
+        ws.apply(table_p, count=True, overwrite=True)
+        fb, spilled, dropped = _part_meta(ws)
+        assert torch.equal(table_p.view(-1, 2, 1 << 15)[:, 0, :], table_d.view(-1, 2, 1 << 15)[:, 0, :]), shift
+        assert fb == 0 and not dropped and spilled < 0.02 * pr.total_bases, (shift, fb, spilled, dropped)
+    # the cell capacities really differ: AT-rich cells got several times the capacity of GC-rich ones
+    ncell = ws.part.n_buckets << (ws.part.shift - 16)
+    words = ws.sub.view(torch.int32)[ws.part.l2_cells0 // 2: ws.part.l2_cells0 // 2 + 3 * ncell + 1].cpu().numpy().view(np.uint32)
+    cap = words[ncell + 1: 2 * ncell + 1].astype(np.int64)
+    assert cap.max() >= 4 * max(int(np.median(cap)), 1) and cap.min() >= 8, (cap.min(), np.median(cap), cap.max())
+    off = words[:ncell + 1].astype(np.int64)
+    assert np.array_equal(np.diff(off), cap * ws.part.l2_ncta // 8) and off[-1] * 8 <= ws.part.l2_span
+
+
 def test_multi_gpu_exchange_building_blocks_on_one_device():
     """The pieces of dist.PeerExchange on one GPU: two read shards counted into two private tables ("ranks"), the peer's
     canonical rows pulled piece by piece with lrb_dev_copy2d into a staging plane, added with lrb_dev_add_planes, and every

@@ -22,15 +22,34 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=200000)
 ap.add_argument("--fractions", default="0,0.01,0.05,0.2")
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--gc", default="", help="comma-separated GC contents: additional sets drawn from genomes of that base composition "
+                                         "(e.g. 0.3,0.2): a skewed KEY distribution over the (bucket, sub-slice) cells without hot keys")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 k, P, BS, BC = 4, COMP_WIDTH[4], 32, 10
 spec = SynthSpec(a.reads, lengths="gamma5k", errors="ont", seed=22)
 base = spec.host_sequences()
 rng = np.random.default_rng(3)
-for frac in [float(x) for x in a.fractions.split(",")]:
-    seqs = list(base)
-    n_low = int(frac * len(seqs))
+def gc_reads(gc, lengths, rng):
+    """error-free reads, both strands, from one 20 Mbp genome with P(G) = P(C) = gc / 2"""
+    p = [(1 - gc) / 2, gc / 2, (1 - gc) / 2, gc / 2]                 # A C T G in code order
+    genome = rng.choice(np.frombuffer(b"ACTG", dtype=np.uint8), size=20_000_000, p=p)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    out = []
+    for L in lengths:
+        st = int(rng.integers(0, len(genome) - int(L)))
+        r = genome[st:st + int(L)]
+        if rng.random() < 0.5:
+            r = comp[r[::-1]]
+        out.append(r.tobytes())
+    return out
+
+
+sets = [("low_complexity", float(x)) for x in a.fractions.split(",") if x != ""] + [("gc", float(x)) for x in a.gc.split(",") if x != ""]
+for kind, frac in sets:
+    seqs = list(base) if kind == "low_complexity" else gc_reads(frac, spec.lengths, rng)
+    n_low = int(frac * len(seqs)) if kind == "low_complexity" else 0
     for i in rng.choice(len(seqs), size=n_low, replace=False):
         L = len(seqs[i])
         if rng.random() < 0.3:
@@ -73,7 +92,7 @@ for frac in [float(x) for x in a.fractions.split(",")]:
     spill_n = int(meta[2 * 64 * 64 + 65 + 2 + 32])
     V = int(sums.to(torch.int64).sum().item())
     assert int(hist.to(torch.int64).sum().item()) == V
-    print(json.dumps({"low_complexity_fraction": frac, "reads": n, "bases": Lb, "valid_windows": V, "ms_per_step": ms,
+    print(json.dumps({("low_complexity_fraction" if kind == "low_complexity" else "genome_gc_content"): frac, "reads": n, "bases": Lb, "valid_windows": V, "ms_per_step": ms,
                       "Gbases_per_s": Lb / ms / 1e6, "buckets_counted_by_L2_atomics": int(o2[:ws.part.n_buckets].astype(bool).sum()), "entries_through_the_spill_area": spill_n,
                       "kernel_ms_per_step": {kk: round(v[1] / a.steps, 3) for kk, v in prof.items() if v[1] / a.steps >= 0.01}}), flush=True)
     del ws, table, comp, hist, sums, dr, pr
