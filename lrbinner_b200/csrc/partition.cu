@@ -1179,7 +1179,9 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
         if (c == 0) {   // segment capacities from the key distribution of a sample of the first chunk (see L2Layout)
             const uint64_t stride = std::max<uint64_t>(1, nblk >> 21);
             const uint64_t n_samp = (nblk + stride - 1) / stride;
-            if (full)
+            static const bool uniform_caps = getenv("LRB_K2_UNIFORM") && atoi(getenv("LRB_K2_UNIFORM")) > 0;   // experiment: no sample -> one capacity for all cells
+            if (uniform_caps) {
+            } else if (full)
                 LRB_LAUNCH("k_sample_cells", st, k_sample_cells<true><<<(unsigned)((n_samp + 255) / 256), 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, stride, part->key_lo, part->key_hi, part->sub, Y));
             else
                 LRB_LAUNCH("k_sample_cells", st, k_sample_cells<false><<<(unsigned)((n_samp + 255) / 256), 256, 0, st>>>(dev->codes, dev->valid, blk_lo, blk_hi, stride, part->key_lo, part->key_hi, part->sub, Y));
