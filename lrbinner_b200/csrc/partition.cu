@@ -444,11 +444,15 @@ struct L2Layout {
     // GC-skewed community fills its segments as evenly as a uniform one (round 1 / early round 2 gave every cell the same
     // capacity and leaned on the fallback / spill area).  Too small a sample -> the uniform C3.
     uint64_t seg0, seg_units;       // first segment; u16 units available for segments
-    uint64_t cells0;                // u16 offset of the cell table: u32 cell_off[ncell + 1], u32 cell_cap[ncell], u32 cell_hist[ncell]
+    uint64_t cells0;                // u16 offset of the cell table: u32 cell_off[ncell + 1], cell_cap[ncell], cell_hist[ncell], run_len[nb]
+    uint64_t windows_est;           // upper estimate of the windows the whole partition will hold (its list capacity)
     __host__ __device__ uint32_t ncell() const { return nb * nsub; }
     __device__ const uint32_t* cell_off(const uint16_t* ws) const { return reinterpret_cast<const uint32_t*>(ws + cells0); }
     __device__ const uint32_t* cell_cap(const uint16_t* ws) const { return cell_off(ws) + ncell() + 1; }
     __device__ uint32_t* cell_hist(uint16_t* ws) const { return reinterpret_cast<uint32_t*>(ws + cells0) + 2 * ncell() + 1; }
+    // tiles of bucket b a k2_partition CTA takes per visit (<= kL2Run; shorter for small buckets, so that every CTA still
+    // gets its share of the bucket and no (cell, CTA) segment sees much more than the mean)
+    __device__ const uint32_t* run_len(const uint16_t* ws) const { return reinterpret_cast<const uint32_t*>(ws + cells0) + 3 * ncell() + 1; }
     // spill area: full table keys (u32) of the entries that found their staging row, the tile's overflow list or their
     // segment full (hot keys: low-complexity reads put thousands of equal windows into one tile); applied with warp-
     // aggregated REDs by k_count_spill after the shared-memory count
@@ -477,16 +481,28 @@ k_sample_cells(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ 
     for_each_key<FULL>(b, key_lo, key_hi, [&](uint32_t kk) { atomicAdd(hist + ((kk - key_lo) >> 16), 1u); });
 }
 
-// one CTA: capacities and offsets of all cells from the sampled histogram
+// one CTA: run lengths, capacities and offsets of all cells from the sampled histogram.
+// A CTA of k2_partition receives bucket b in RUNS of run_len[b] tiles, cyclically over the CTAs, so over the whole input a
+// (cell, CTA) segment gets the cell's mean share per CTA give or take ONE run.  Capacity of a cell's segments therefore =
+// floor + its share of the space that is left + one run's worth of the cell (run_len[b] * 8192 * share inside b).
 __global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, L2Layout Y) {
     __shared__ ull s_red[1024];
     __shared__ ull s_scan[1024];
+    __shared__ ull s_bsum[kMaxBuckets];
+    __shared__ uint32_t s_rl[kMaxBuckets];
+    __shared__ ull s_slack;
     const uint32_t tid = threadIdx.x, ncell = Y.ncell();
     uint32_t* off = const_cast<uint32_t*>(Y.cell_off(ws));
     uint32_t* cap = const_cast<uint32_t*>(Y.cell_cap(ws));
+    uint32_t* rl = const_cast<uint32_t*>(Y.run_len(ws));
     const uint32_t* hist = Y.cell_hist(ws);
+    if (tid < (uint32_t)kMaxBuckets) s_bsum[tid] = 0;
+    __syncthreads();
     ull sum = 0;
-    for (uint32_t c = tid; c < ncell; c += 1024) sum += hist[c];
+    for (uint32_t c = tid; c < ncell; c += 1024) {
+        sum += hist[c];
+        atomicAdd(&s_bsum[c / Y.nsub], (ull)hist[c]);
+    }
     s_red[tid] = sum;
     __syncthreads();
     for (int d = 512; d > 0; d >>= 1) {
@@ -494,18 +510,37 @@ __global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, 
         __syncthreads();
     }
     const ull total = s_red[0];
-    // per-CTA entries to hand out beyond the floor; a bucket's segments must stay below 2^32 u16 units (32-bit row offsets)
-    const ull per_cta = Y.seg_units / Y.n_cta;
+    const ull per_cta = Y.seg_units / Y.n_cta;   // entries a CTA can be given over all cells
     const ull floor_all = (ull)ncell * kCellFloor;
-    const bool uniform = total < 32ull * ncell || per_cta <= floor_all;
-    const ull avail = uniform ? 0ull : per_cta - floor_all;
-    const ull clamp = ((1ull << 32) - 8 - kStepSlots) / ((ull)Y.nsub * Y.n_cta);
+    bool uniform = total < 32ull * ncell || per_cta <= floor_all;
+    if (tid == 0) {
+        ull slack = 0;
+        for (uint32_t bkt = 0; bkt < Y.nb; ++bkt) {
+            // tiles the bucket will hold in the end; at least 4 runs per CTA when the bucket is big enough
+            const ull tiles = uniform ? ~0ull : (ull)((double)s_bsum[bkt] / (double)total * (double)Y.windows_est / kStepSlots);
+            const uint32_t r = (uint32_t)min((ull)kL2Run, max(1ull, tiles / (4ull * Y.n_cta)));
+            s_rl[bkt] = r;
+            slack += (ull)r * kStepSlots;
+        }
+        s_slack = slack;
+    }
+    __syncthreads();
+    if (per_cta <= floor_all + s_slack + (per_cta >> 2)) uniform = true;   // no room for the scheme: one capacity, full runs
+    if (tid < Y.nb) rl[tid] = uniform ? kL2Run : s_rl[tid];
+    const ull avail = uniform ? 0ull : per_cta - floor_all - s_slack;
+    const ull clamp = ((1ull << 32) - 8 - kStepSlots) / ((ull)Y.nsub * Y.n_cta);   // a bucket's segments stay below 2^32 u16 units
     // contiguous stretch of cells per thread, so that one scan over the threads' totals gives every cell its offset
     const uint32_t per = (ncell + 1023u) / 1024u;
     const uint32_t c0 = min(ncell, tid * per), c1 = min(ncell, c0 + per);
     ull mine = 0;
     for (uint32_t c = c0; c < c1; ++c) {
-        ull w = uniform ? (ull)Y.C3 : kCellFloor + (ull)hist[c] * avail / total;
+        ull w;
+        if (uniform) w = Y.C3;
+        else {
+            const uint32_t bkt = c / Y.nsub;
+            const ull one_run = s_bsum[bkt] ? (ull)s_rl[bkt] * kStepSlots * hist[c] / s_bsum[bkt] : 0ull;
+            w = kCellFloor + (ull)hist[c] * avail / total + one_run;
+        }
         w = min(w, clamp) & ~7ull;
         cap[c] = (uint32_t)w;
         mine += w * Y.n_cta / 8;   // octets
@@ -535,7 +570,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     __shared__ uint32_t s_ovl[kL2Ovl];             // (sub << 15) | low key bits of the entries that found their row full
     __shared__ uint32_t s_novl[2];                 // length of s_ovl, by tile parity
     __shared__ uint32_t s_sp2[kMaxSubs];           // entries of the tile per sub-slice that went straight to the spill area (rare)
-    __shared__ uint32_t s_tiles[kMaxBuckets], s_runs[kMaxBuckets], s_start[kMaxBuckets], s_runs0[kMaxBuckets];  // tile schedule (below)
+    __shared__ uint32_t s_tiles[kMaxBuckets], s_runs[kMaxBuckets], s_start[kMaxBuckets], s_runs0[kMaxBuckets], s_rl[kMaxBuckets];  // tile schedule (below)
     __shared__ ull s_reg_n[kMaxBuckets], s_reg_off[kMaxBuckets];
     __shared__ uint32_t s_ovf[kMaxBuckets];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -553,12 +588,14 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         s_reg_off[tid] = tid < Y.nb ? meta->offsets[c][tid] : 0ull;
         const uint32_t tiles = (uint32_t)((n_reg + kStepSlots - 1) / kStepSlots);
         s_tiles[tid] = tiles;
-        s_runs[tid] = (tiles + kL2Run - 1u) / kL2Run;
+        const uint32_t rlen = tid < Y.nb ? max(1u, min((uint32_t)kL2Run, __ldg(Y.run_len(ws) + tid))) : (uint32_t)kL2Run;
+        s_rl[tid] = rlen;
+        s_runs[tid] = (tiles + rlen - 1u) / rlen;
         // runs of this bucket in the earlier chunks, and in chunk 0 (the base spread of the buckets over the CTAs)
         uint32_t before = 0, runs0 = 0;
         if (tid < Y.nb) {
             for (int cc = 0; cc < c; ++cc) {
-                const uint32_t rr = (uint32_t)(((meta->counts[cc][tid] + kStepSlots - 1) / kStepSlots + kL2Run - 1u) / kL2Run);
+                const uint32_t rr = (uint32_t)(((meta->counts[cc][tid] + kStepSlots - 1) / kStepSlots + rlen - 1u) / rlen);
                 before += rr;
                 if (cc == 0) runs0 = rr;
             }
@@ -592,7 +629,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         return false;
     };
     auto advance = [&]() {
-        if (++gt < kL2Run && gr * kL2Run + gt < s_tiles[gb]) return true;
+        if (++gt < s_rl[gb] && gr * s_rl[gb] + gt < s_tiles[gb]) return true;
         gt = 0;
         gr += n_cta;
         if (gr < s_runs[gb]) return true;
@@ -601,7 +638,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     };
     auto fetch = [&](uint32_t (&e)[kL2PerThread], uint32_t& b, uint32_t& n_tile) {  // the generator's current tile
         b = gb;
-        const uint32_t t = gr * kL2Run + gt;
+        const uint32_t t = gr * s_rl[b] + gt;
         n_tile = (uint32_t)min((ull)kStepSlots, s_reg_n[b] - (ull)t * kStepSlots);
         const uint32_t* __restrict__ src = ents + s_reg_off[b] + (ull)t * kStepSlots;
         if (n_tile == (uint32_t)kStepSlots) {
@@ -1106,7 +1143,7 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
         // workspace (u16 units): fill counters | cell table | segments ... spare tile | spill area
         const uint64_t ncell = (uint64_t)nb * nsub;
         const uint64_t fill_u16 = (n_cta * ncell * 2 + 7) & ~7ull;               // fill counters (u32)
-        const uint64_t cells_u16 = ((3 * ncell + 1) * 2 + 7) & ~7ull;            // cell_off[ncell+1], cell_cap[ncell], cell_hist[ncell] (u32)
+        const uint64_t cells_u16 = ((3 * ncell + 1 + kMaxBuckets) * 2 + 7) & ~7ull;   // cell_off[ncell+1], cell_cap[ncell], cell_hist[ncell], run_len[nb] (u32)
         const uint64_t seg0 = fill_u16 + cells_u16;
         const uint64_t segs = ncell * n_cta;
         // spill area (u32 keys) at the end of the workspace: 1/8 of the list capacity, i.e. 1/8 of ALL windows may sit in
@@ -1174,10 +1211,10 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
     if (part->l2_enabled) {
         L2Layout Y;
         Y.nsub = 1u << (shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)nb; Y.strided = l2_strided();
-        Y.seg0 = part->l2_seg0; Y.seg_units = part->l2_span; Y.cells0 = part->l2_cells0;
+        Y.seg0 = part->l2_seg0; Y.seg_units = part->l2_span; Y.cells0 = part->l2_cells0; Y.windows_est = part->capacity;
         Y.spill0 = part->l2_spill0; Y.spill_cap = part->l2_spill_cap; Y.key_lo = part->key_lo; Y.shift = shift;
         if (c == 0) {   // segment capacities from the key distribution of a sample of the first chunk (see L2Layout)
-            const uint64_t stride = std::max<uint64_t>(1, nblk >> 21);
+            const uint64_t stride = std::max<uint64_t>(1, nblk >> 18);   // <= 2^18 blocks = 8 M windows: ~500 per cell, 0.1 ms
             const uint64_t n_samp = (nblk + stride - 1) / stride;
             static const bool uniform_caps = getenv("LRB_K2_UNIFORM") && atoi(getenv("LRB_K2_UNIFORM")) > 0;   // experiment: no sample -> one capacity for all cells
             if (uniform_caps) {
@@ -1265,7 +1302,7 @@ extern "C" int lrb_dev_partition_apply_range(const lrb_partition* part, int mode
     L2Layout Y = {};
     if (smem_count) {
         Y.nsub = 1u << (part->shift - 16); Y.n_cta = part->l2_ncta; Y.C3 = part->l2_C3; Y.nb = (uint32_t)part->n_buckets; Y.strided = l2_strided();
-        Y.seg0 = part->l2_seg0; Y.seg_units = part->l2_span; Y.cells0 = part->l2_cells0;
+        Y.seg0 = part->l2_seg0; Y.seg_units = part->l2_span; Y.cells0 = part->l2_cells0; Y.windows_est = part->capacity;
         Y.spill0 = part->l2_spill0; Y.spill_cap = part->l2_spill_cap; Y.key_lo = part->key_lo; Y.shift = part->shift;
     }
     if (do_search) {

@@ -604,7 +604,7 @@ def test_second_level_count_survives_key_skew():
     # the homopolymers (290 000 windows of one key) cannot fit any list segment: they went through the spill area, and no
     # bucket had to fall back
     assert fell_back[24] == 0 and fell_back[25] == 0, fell_back
-    assert spilled[24] > 200000 and spilled[25] > 200000, spilled
+    assert spilled[24] > 150000 and spilled[25] > 150000, spilled
     # a read set DOMINATED by one key overflows the spill area (1/8 of the list capacity): its bucket falls back to the
     # (aggregating) L2-atomic kernel, the other buckets still go through shared memory; adding and writing forms
     seqs2 = seqs[:600] + [b"A" * 6000] * 400
