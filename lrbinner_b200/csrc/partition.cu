@@ -444,15 +444,18 @@ struct L2Layout {
     // GC-skewed community fills its segments as evenly as a uniform one (round 1 / early round 2 gave every cell the same
     // capacity and leaned on the fallback / spill area).  Too small a sample -> the uniform C3.
     uint64_t seg0, seg_units;       // first segment; u16 units available for segments
-    uint64_t cells0;                // u16 offset of the cell table: u32 cell_off[ncell + 1], cell_cap[ncell], cell_hist[ncell], run_len[nb]
+    // cell table (u16 offset cells0): uint2 info[ncell] = {offset in octets, capacity}, u32 hist[ncell], u32 run_len[nb].
+    // info of cell (b, sub) sits at b * nsub + cell_pos(sub): the permutation of the fill rows, so that the 16 rows a
+    // k2_partition warp owns are one 128-byte load (in natural order they are 16 sectors: +25 % l1tex wavefronts per tile)
+    uint64_t cells0;
     uint64_t windows_est;           // upper estimate of the windows the whole partition will hold (its list capacity)
     __host__ __device__ uint32_t ncell() const { return nb * nsub; }
-    __device__ const uint32_t* cell_off(const uint16_t* ws) const { return reinterpret_cast<const uint32_t*>(ws + cells0); }
-    __device__ const uint32_t* cell_cap(const uint16_t* ws) const { return cell_off(ws) + ncell() + 1; }
-    __device__ uint32_t* cell_hist(uint16_t* ws) const { return reinterpret_cast<uint32_t*>(ws + cells0) + 2 * ncell() + 1; }
+    __host__ __device__ uint32_t cell_pos(uint32_t sub) const { return strided ? fill_pos(sub) : sub; }
+    __device__ const uint2* cell_info(const uint16_t* ws) const { return reinterpret_cast<const uint2*>(ws + cells0); }
+    __device__ uint32_t* cell_hist(uint16_t* ws) const { return reinterpret_cast<uint32_t*>(ws + cells0) + 2 * ncell(); }
     // tiles of bucket b a k2_partition CTA takes per visit (<= kL2Run; shorter for small buckets, so that every CTA still
     // gets its share of the bucket and no (cell, CTA) segment sees much more than the mean)
-    __device__ const uint32_t* run_len(const uint16_t* ws) const { return reinterpret_cast<const uint32_t*>(ws + cells0) + 3 * ncell() + 1; }
+    __device__ const uint32_t* run_len(const uint16_t* ws) const { return reinterpret_cast<const uint32_t*>(ws + cells0) + 3 * ncell(); }
     // spill area: full table keys (u32) of the entries that found their staging row, the tile's overflow list or their
     // segment full (hot keys: low-complexity reads put thousands of equal windows into one tile); applied with warp-
     // aggregated REDs by k_count_spill after the shared-memory count
@@ -492,9 +495,9 @@ __global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, 
     __shared__ uint32_t s_rl[kMaxBuckets];
     __shared__ ull s_slack;
     const uint32_t tid = threadIdx.x, ncell = Y.ncell();
-    uint32_t* off = const_cast<uint32_t*>(Y.cell_off(ws));
-    uint32_t* cap = const_cast<uint32_t*>(Y.cell_cap(ws));
+    uint2* info = const_cast<uint2*>(Y.cell_info(ws));
     uint32_t* rl = const_cast<uint32_t*>(Y.run_len(ws));
+    auto slot = [&](uint32_t c) { return (c / Y.nsub) * Y.nsub + Y.cell_pos(c % Y.nsub); };
     const uint32_t* hist = Y.cell_hist(ws);
     if (tid < (uint32_t)kMaxBuckets) s_bsum[tid] = 0;
     __syncthreads();
@@ -528,6 +531,7 @@ __global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, 
     if (per_cta <= floor_all + s_slack + (per_cta >> 2)) uniform = true;   // no room for the scheme: one capacity, full runs
     if (tid < Y.nb) rl[tid] = uniform ? kL2Run : s_rl[tid];
     const ull avail = uniform ? 0ull : per_cta - floor_all - s_slack;
+    const double share_scale = uniform ? 0.0 : (double)avail / (double)total * 0.999;   // 0.999: rounding never hands out more than there is
     const ull clamp = ((1ull << 32) - 8 - kStepSlots) / ((ull)Y.nsub * Y.n_cta);   // a bucket's segments stay below 2^32 u16 units
     // contiguous stretch of cells per thread, so that one scan over the threads' totals gives every cell its offset
     const uint32_t per = (ncell + 1023u) / 1024u;
@@ -538,11 +542,12 @@ __global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, 
         if (uniform) w = Y.C3;
         else {
             const uint32_t bkt = c / Y.nsub;
-            const ull one_run = s_bsum[bkt] ? (ull)s_rl[bkt] * kStepSlots * hist[c] / s_bsum[bkt] : 0ull;
-            w = kCellFloor + (ull)hist[c] * avail / total + one_run;
+            const double h = (double)hist[c];   // doubles: 16 K 64-bit divisions in one CTA would be most of this kernel's time
+            const double one_run = s_bsum[bkt] ? (double)s_rl[bkt] * kStepSlots * h / (double)s_bsum[bkt] : 0.0;
+            w = kCellFloor + (ull)(h * share_scale) + (ull)one_run;
         }
         w = min(w, clamp) & ~7ull;
-        cap[c] = (uint32_t)w;
+        info[slot(c)].y = (uint32_t)w;
         mine += w * Y.n_cta / 8;   // octets
     }
     s_scan[tid] = mine;
@@ -554,11 +559,10 @@ __global__ void __launch_bounds__(1024) k_plan_cells(uint16_t* __restrict__ ws, 
         __syncthreads();
     }
     ull acc = s_scan[tid] - mine;
-    for (uint32_t c = c0; c < c1; ++c) {
-        off[c] = (uint32_t)acc;
-        acc += (ull)cap[c] * Y.n_cta / 8;
+    for (uint32_t c = c0; c < c1; ++c) {   // natural order: cell (b, 0) has the lowest offset of bucket b
+        info[slot(c)].x = (uint32_t)acc;
+        acc += (ull)info[slot(c)].y * Y.n_cta / 8;
     }
-    if (tid == 1023) off[ncell] = (uint32_t)s_scan[1023];
 }
 
 template <int LOG2_NSUB, bool STRIDED>
@@ -651,8 +655,7 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
     };
     const uint32_t stage_mask = (nsub << kSubBits) - 1u;  // sub-slice index + low key bits, as they sit in the entry
     uint32_t* __restrict__ spill_keys = reinterpret_cast<uint32_t*>(ws + Y.spill0);
-    const uint32_t* __restrict__ c_off = Y.cell_off(ws);
-    const uint32_t* __restrict__ c_cap = Y.cell_cap(ws);
+    const uint2* __restrict__ c_info = Y.cell_info(ws);
     // n keys of this warp into the spill area: one reservation per call (warp-aggregated), keys produced by key_at(i).
     // When the area is full the remaining keys are dropped and the bucket is flagged: k_count_keys then counts the whole
     // bucket from the first-level list and both other count kernels skip it.
@@ -681,9 +684,10 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
         const uint32_t f_my = lane < spw ? frow[my_pos] : 0u;    // written only by this lane (previous tiles of this CTA)
         // this row's segment: capacity and position relative to the bucket's first segment
         const uint32_t cell0 = b_cur * nsub;
-        const uint32_t cap_my = lane < spw ? __ldg(c_cap + cell0 + my_sub) : 0u;
-        const uint32_t boff0 = __ldg(c_off + cell0);
-        const uint32_t rel_my = lane < spw ? (__ldg(c_off + cell0 + my_sub) - boff0) * 8u + blockIdx.x * cap_my : 0u;
+        const uint2 ci_my = lane < spw ? __ldg(c_info + cell0 + my_pos) : make_uint2(0u, 0u);   // the warp's rows: one 128-byte stretch
+        const uint32_t boff0 = __ldg(&c_info[cell0].x);
+        const uint32_t cap_my = ci_my.y;
+        const uint32_t rel_my = (ci_my.x - boff0) * 8u + blockIdx.x * cap_my;
         // place: one returning atomic + one predicated 2-byte store per entry (the staged half-word keeps entry bit 15, a
         // sub-slice bit: k_count_smem masks it off); entries that find their row full are remembered in a bit mask and go
         // to the overflow list afterwards
@@ -704,13 +708,14 @@ k2_partition(const uint32_t* __restrict__ ents, PartMeta* __restrict__ meta, int
                 if (j * kL2Threads + tid < n_cur) place(j);
         }
         uint32_t spill2 = 0;   // entries that missed the overflow list as well: straight to the spill area
-        if (spill) {
+        if (spill) {   // one reservation per thread (the list counter is a single address: hot cells would serialise on it)
+            uint32_t o = atomicAdd(&s_novl[par], (uint32_t)__popc(spill));
 #pragma unroll
             for (int j = 0; j < kL2PerThread; ++j) {
                 if ((spill >> j) & 1u) {
-                    const uint32_t o = atomicAdd(&s_novl[par], 1u);
                     if (o < (uint32_t)kL2Ovl) s_ovl[o] = e[j] & stage_mask;
                     else spill2 |= 1u << j;
+                    ++o;
                 }
             }
         }
@@ -874,9 +879,9 @@ k_count_smem(const uint16_t* __restrict__ ws, const PartMeta* __restrict__ meta,
     }
     const uint32_t* __restrict__ fill = reinterpret_cast<const uint32_t*>(ws) + (size_t)bucket * Y.nsub + (Y.strided ? Y.fill_pos(sub) : sub);  // + cta * nb * nsub
     const size_t fill_stride = (size_t)Y.nb * Y.nsub;
-    const uint32_t cell = (uint32_t)bucket * Y.nsub + sub;
-    const uint32_t seg_cap = __ldg(Y.cell_cap(ws) + cell);
-    const uint16_t* __restrict__ lists = ws + Y.seg0 + 8ull * __ldg(Y.cell_off(ws) + cell);   // this cell's n_cta segments
+    const uint2 ci = __ldg(Y.cell_info(ws) + (uint32_t)bucket * Y.nsub + Y.cell_pos(sub));
+    const uint32_t seg_cap = ci.y;
+    const uint16_t* __restrict__ lists = ws + Y.seg0 + 8ull * ci.x;   // this cell's n_cta segments
     uint4* tab4 = reinterpret_cast<uint4*>(s_tab);
     for (uint32_t i = tid; i < (1u << kSubBits) / 4; i += 1024) tab4[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -1143,7 +1148,7 @@ extern "C" int lrb_dev_partition_begin(lrb_partition* part, int with_rids, uint3
         // workspace (u16 units): fill counters | cell table | segments ... spare tile | spill area
         const uint64_t ncell = (uint64_t)nb * nsub;
         const uint64_t fill_u16 = (n_cta * ncell * 2 + 7) & ~7ull;               // fill counters (u32)
-        const uint64_t cells_u16 = ((3 * ncell + 1 + kMaxBuckets) * 2 + 7) & ~7ull;   // cell_off[ncell+1], cell_cap[ncell], cell_hist[ncell], run_len[nb] (u32)
+        const uint64_t cells_u16 = ((3 * ncell + kMaxBuckets) * 2 + 7) & ~7ull;   // uint2 info[ncell], u32 hist[ncell], u32 run_len[nb]
         const uint64_t seg0 = fill_u16 + cells_u16;
         const uint64_t segs = ncell * n_cta;
         // spill area (u32 keys) at the end of the workspace: 1/8 of the list capacity, i.e. 1/8 of ALL windows may sit in

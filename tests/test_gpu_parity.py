@@ -652,12 +652,16 @@ def test_segment_capacities_follow_the_key_distribution():
         assert torch.equal(table_p.view(-1, 2, 1 << 15)[:, 0, :], table_d.view(-1, 2, 1 << 15)[:, 0, :]), shift
         assert fb == 0 and not dropped and spilled < 0.02 * pr.total_bases, (shift, fb, spilled, dropped)
     # the cell capacities really differ: AT-rich cells got several times the capacity of GC-rich ones
-    ncell = ws.part.n_buckets << (ws.part.shift - 16)
-    words = ws.sub.view(torch.int32)[ws.part.l2_cells0 // 2: ws.part.l2_cells0 // 2 + 3 * ncell + 1].cpu().numpy().view(np.uint32)
-    cap = words[ncell + 1: 2 * ncell + 1].astype(np.int64)
+    # cell table (csrc/partition.cu, L2Layout): uint2 {offset in octets, capacity} per cell, rows permuted inside a bucket
+    nsub = 1 << (ws.part.shift - 16)
+    ncell = ws.part.n_buckets * nsub
+    words = ws.sub.view(torch.int32)[ws.part.l2_cells0 // 2: ws.part.l2_cells0 // 2 + 2 * ncell].cpu().numpy().view(np.uint32)
+    sub = np.arange(nsub)
+    pos = (sub & 15) * (nsub >> 4) + (sub >> 4)
+    slot = (np.arange(ws.part.n_buckets)[:, None] * nsub + pos[None, :]).reshape(-1)        # natural (bucket, sub) order -> table slot
+    off, cap = words[0::2][slot].astype(np.int64), words[1::2][slot].astype(np.int64)
     assert cap.max() >= 4 * max(int(np.median(cap)), 1) and cap.min() >= 8, (cap.min(), np.median(cap), cap.max())
-    off = words[:ncell + 1].astype(np.int64)
-    assert np.array_equal(np.diff(off), cap * ws.part.l2_ncta // 8) and off[-1] * 8 <= ws.part.l2_span
+    assert np.array_equal(np.diff(off), (cap * ws.part.l2_ncta // 8)[:-1]) and (off[-1] + cap[-1] * ws.part.l2_ncta // 8) * 8 <= ws.part.l2_span
 
 
 def test_multi_gpu_exchange_building_blocks_on_one_device():
