@@ -128,6 +128,27 @@ __global__ void __launch_bounds__(256) k_mirror(uint32_t* __restrict__ table) {
     for (uint32_t a = ty; a < 64; a += 4) table[mirror_dst_index(t, a, tx)] = tile[rc_small(tx, 3)][rc_small(a, 3)];
 }
 
+// the same with 16-byte global accesses: a source row of the tile is 64 contiguous entries = 16 uint4, and so is a
+// destination row; a quarter of the LDG / STG instructions for the same bytes
+__global__ void __launch_bounds__(256) k_mirror_v4(uint32_t* __restrict__ table) {
+    __shared__ uint32_t tile[64][65];
+    const uint32_t t = blockIdx.x;
+    const uint32_t c4 = (threadIdx.x & 15u) * 4u, r = threadIdx.x >> 4;  // 16 uint4 columns x 16 rows per pass
+#pragma unroll
+    for (uint32_t sb = r; sb < 64; sb += 16) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(table + mirror_src_index(t, sb, c4)));
+        tile[sb][c4] = v.x; tile[sb][c4 + 1] = v.y; tile[sb][c4 + 2] = v.z; tile[sb][c4 + 3] = v.w;
+    }
+    __syncthreads();
+    const uint32_t s0 = rc_small(c4, 3), s1 = rc_small(c4 + 1, 3), s2 = rc_small(c4 + 2, 3), s3 = rc_small(c4 + 3, 3);
+#pragma unroll
+    for (uint32_t a = r; a < 64; a += 16) {
+        const uint32_t col = rc_small(a, 3);
+        const uint4 o = make_uint4(tile[s0][col], tile[s1][col], tile[s2][col], tile[s3][col]);
+        __stcs(reinterpret_cast<uint4*>(table + mirror_dst_index(t, a, c4)), o);
+    }
+}
+
 // validity bitmap from the read lengths (one warp per read), then the sparse exceptions on top
 __global__ void __launch_bounds__(256) k_default_valid(lrb_reads_view R, uint32_t* __restrict__ valid) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -356,7 +377,9 @@ extern "C" int lrb_dev_count(const lrb_reads_view* dev, uint32_t* table, uint64_
 
 extern "C" int lrb_dev_mirror(uint32_t* table, void* stream) {
     if (!table) return lrb_set_error(LRB_EINVAL, "lrb_dev_mirror: null table");
-    LRB_LAUNCH("k_mirror", (cudaStream_t)stream, k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table));
+    static const bool scalar = getenv("LRB_MIRROR_SCALAR") && atoi(getenv("LRB_MIRROR_SCALAR")) > 0;   // round-1 kernel, for A/B timing
+    if (scalar) LRB_LAUNCH("k_mirror", (cudaStream_t)stream, k_mirror<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table));
+    else LRB_LAUNCH("k_mirror", (cudaStream_t)stream, k_mirror_v4<<<1u << 17, 256, 0, (cudaStream_t)stream>>>(table));
     LRB_CUDA(cudaGetLastError());
     return LRB_OK;
 }

@@ -772,6 +772,56 @@ def _full_size_properties(name, subsample=200):
     del table, comp, hist
 
 
+def test_config1_full_size_all_three_files_against_the_reference_tools():
+    """BASELINE.json config #1 in full (100 k reads, 0.5 Gbases, -k 3 -bs 32 -bc 10): the UNMODIFIED reference tools
+    (oracle/_ref, built from /root/reference and shipped with the repo) and the drop-ins on the same FASTA; com_profs and
+    cov_profs byte for byte, 15mers-counts by sha256 of the whole 4 GiB file — fused call and the three separate calls."""
+    import hashlib
+    import shutil
+    import tempfile
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    cfg = CONFIGS["cfg1_100k_5kb_k3"]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 12 * 2 ** 30 else None
+    work = tempfile.mkdtemp(prefix="lrb_cfg1_", dir=base)
+    try:
+        spec = SynthSpec(cfg["n_reads"], lengths=cfg["lengths"], errors=cfg["errors"], seed=cfg["seed"])
+        fasta = os.path.join(work, "cfg1.fa")
+        write_fasta(fasta, spec.host_sequences())
+        threads = os.cpu_count() or 8
+        ref = {x: os.path.join(work, "ref_" + x) for x in ("com", "tbl", "cov")}
+        oracle.ref_count_kmers(fasta, ref["com"], cfg["k"], threads)
+        oracle.ref_count_15mers(fasta, ref["tbl"], threads)
+        oracle.ref_search_15mers(ref["tbl"], fasta, ref["cov"], 32, 10, threads)
+
+        def sha(path):
+            h = hashlib.sha256()
+            with open(path, "rb") as f:
+                for blk in iter(lambda: f.read(1 << 24), b""):
+                    h.update(blk)
+            return h.hexdigest()
+
+        want_tbl = sha(ref["tbl"])
+        os.remove(ref["tbl"])
+        want_com, want_cov = open(ref["com"], "rb").read(), open(ref["cov"], "rb").read()
+        assert len(want_com) == cfg["n_reads"] * (32 * 9 + 1) and len(want_cov) == cfg["n_reads"] * 90
+        out = os.path.join(work, "fused")
+        runners_utils.run_profile(fasta, out, cfg["k"], 32, 10, threads, write_table=True)
+        assert open(f"{out}/profiles/com_profs", "rb").read() == want_com
+        assert open(f"{out}/profiles/cov_profs", "rb").read() == want_cov
+        assert sha(f"{out}/profiles/15mers-counts") == want_tbl
+        shutil.rmtree(out)
+        out = os.path.join(work, "three")
+        runners_utils.run_kmers(fasta, out, cfg["k"], threads)
+        runners_utils.run_15mer_counts(fasta, out, threads)
+        runners_utils.run_15mer_vecs(fasta, out, 32, 10, threads)
+        assert open(f"{out}/profiles/com_profs", "rb").read() == want_com
+        assert open(f"{out}/profiles/cov_profs", "rb").read() == want_cov
+        assert sha(f"{out}/profiles/15mers-counts") == want_tbl
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def test_full_size_properties_config1():
     _full_size_properties("cfg1_100k_5kb_k3")
 
