@@ -235,6 +235,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     prof = _lib.prof_report()
     clocks = sampler.stop()
     eng.verify()                                         # the partition lists of the timed steps fitted their workspace
+    exchange_t = px.timings() if (px is not None and best.endswith("/p2p")) else None   # last timed step, rank 0
     tot = torch.stack([res["sums"].to(torch.int64).sum(), res["hist"].to(torch.int64).sum()])
     dist.all_reduce(tot)
     valid_windows = int(tot[0].item())
@@ -395,7 +396,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
                     "box_h2d_ceiling_GBps_all_ranks_copying": h2d_peak,
                     "h2d_floor_ms": h2d * world / h2d_peak / 1e6 if h2d_peak else None},
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "verify": verify,
-            "phases_ms_rank0": phases, "clocks": clocks, "cpu_baseline": None, "cpu_affinity": affinity}
+            "phases_ms_rank0": phases, "exchange_rank0": exchange_t, "clocks": clocks, "cpu_baseline": None, "cpu_affinity": affinity}
     S.close()
     del S, eng, dr, layout, res
 
@@ -431,6 +432,7 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
                 "plan": b2, "plan_ms": pm, "plan_ms_every_step": every, "ms_per_step": pm[b2], "value": S2.L / pm[b2] / 1e6, "unit": "Gbases/s",
                 "timing": "median of 5 single steps, each bracketed by barrier + synchronize, max over ranks",
                 "phases_ms_rank0": ph[b2], "plan_phases_ms_rank0": ph, "verify": v2,
+                "exchange_rank0": (px.timings() if (px is not None and b2.endswith("/p2p")) else None),
                 "load_imbalance_max_over_mean_slots": float(mx.item()) / (float(own_bases.item()) / world)})
             S2.close()
             del S2, r2

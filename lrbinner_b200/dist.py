@@ -312,7 +312,7 @@ class PeerExchange:
         row_bytes, pitch_bytes = 4 * self.cols, 8 * self.cols
         my_rows = lambda r0: C.c_void_p(table.data_ptr() + r0 * pitch_bytes)
         peer_rows = lambda p, r0: C.c_void_p(self.peer_table[p].data_ptr() + r0 * pitch_bytes)
-        ready = torch.cuda.Event()
+        ready = torch.cuda.Event(enable_timing=True)
         ready.record(main)
         comm.wait_event(ready)
         events = []
@@ -333,7 +333,7 @@ class PeerExchange:
                     if g < G:
                         r0, r1 = span[g]
                         self.check(self.lib.lrb_dev_copy2d(my_rows(r0), pitch_bytes, peer_rows(p, r0), pitch_bytes, row_bytes, r1 - r0, st))
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(enable_timing=True)
                 ev.record(comm)
                 events.append(ev)
             if self.mirror_beside:
@@ -344,11 +344,23 @@ class PeerExchange:
             if hi > lo:                                       # the round's buckets are contiguous: one launch
                 engine.search_slice(table, bin_size, bins, hist_all, sums_all, lo, hi, pieces[rounds[k][0][0]][0], pieces[rounds[k][-1][0]][1])
         main.wait_stream(comm)
+        self.last_events = (ready, events[0], events[-1]) if events else None   # timings(): after a synchronize
         if not self.mirror_beside:
             # after the search, not beside it: the mirror streams 4 GiB through L2 and evicts the search's resident table
             # slice (single GPU, profiles/r02_exp1_variants.jsonl: search 20.5 -> 26.2 ms with the mirror beside it)
             engine.mirror(table)
 
+
+def _peer_exchange_timings(self):
+    """(ms from count done to the first round's rows being final here = what the search has to wait for,
+        ms from count done to the last round = length of the whole exchange on the copy stream) of the last run()."""
+    if not getattr(self, "last_events", None):
+        return None
+    ready, first, last = self.last_events
+    return {"first_round_ms": ready.elapsed_time(first), "whole_exchange_ms": ready.elapsed_time(last)}
+
+
+PeerExchange.timings = _peer_exchange_timings
 
 _SIDE = {}
 
