@@ -283,6 +283,12 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         cr = None
     copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     marks = {}
+    # Two device buffers for the packed stream (LRB_E2E_BUFFERS=1: one): the host links are the bottleneck of the e2e step
+    # at N >= 4 (box ceiling measured below), so the H2D of step i+1 starts the moment the H2D of step i has finished and
+    # the copy stream never idles; a buffer is free again once the key partition of the step before last is built.
+    n_buf = 2 if (cr is not None and len(cr) >= 2 and os.environ.get("LRB_E2E_BUFFERS", "2") != "1") else 1
+    codes_bufs = [dr.codes] + [torch.empty_like(dr.codes) for _ in range(n_buf - 1)]
+    free_ev, step_no = [], [0]
 
     def e2e_step():
         main = torch.cuda.current_stream()
@@ -300,9 +306,17 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
         start = torch.cuda.Event(enable_timing=True)
         start.record(main)
         marks["start"] = start
-        # the packed stream is dead once the key partition of the previous step is built (count and search work from the
-        # lists): this step's H2D starts there, BESIDE the previous step's exchange + search, not after them
-        copy_in.wait_event(marks.get("codes_free", start))
+        # the packed stream is dead once the key partition of a step is built (count and search work from the lists): the
+        # H2D into a buffer starts when the last step that used THAT buffer has built its partition — BESIDE the exchange +
+        # search of the steps in flight, not after them
+        j_step = step_no[0]
+        step_no[0] += 1
+        buf = codes_bufs[j_step % n_buf]
+        dr.codes = buf
+        dr.view.codes = buf.data_ptr()
+        copy_in.wait_event(free_ev[j_step - n_buf] if j_step >= n_buf else start)
+        if "valid_built" in marks:
+            copy_in.wait_event(marks["valid_built"])       # the previous step has consumed the exception lists
         copy_out.wait_event(start)
         evs = []
         with torch.cuda.stream(copy_in):
@@ -321,12 +335,14 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
             marks["h2d"] = evs[-1]
         main.wait_event(ev0)
         dev_fill_valid(dr, d_exc[0] if len(exc_blk) else None, d_exc[1] if len(exc_blk) else None)
+        marks["valid_built"] = torch.cuda.Event()
+        marks["valid_built"].record(main)
         feed = [(cr[j], cr[j + 1], (lambda j=j: main.wait_event(evs[j]))) for j in range(len(cr) - 1)]
 
         def comp_home(comp):
             ready = torch.cuda.Event()
             ready.record(main)                 # composition + partition + count are enqueued: nothing later reads codes / valid
-            marks["codes_free"] = ready
+            free_ev.append(ready)
             with torch.cuda.stream(copy_out):
                 copy_out.wait_event(ready)
                 out_h["comp"].copy_(comp, non_blocking=True)
@@ -358,8 +374,8 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
     if e2e_phases is not None:
         e2e_phases["phases"] = marks["tm"].phases_ms()
         e2e_phases["h2d_copy_ms"] = marks["h2d_begin"].elapsed_time(marks["h2d"])
-        e2e_phases["note"] = ("h2d = when this step's last chunk landed, relative to the step's start on the compute stream: the copy starts as soon "
-                              "as the previous step's key partition is built (its exchange + search do not read the packed stream)")
+        e2e_phases["note"] = ("h2d = when this step's last chunk landed, relative to the step's start on the compute stream (the copy starts "
+                              "during earlier steps); h2d_copy_ms = first to last chunk on the copy stream")
     # rows of the e2e step are the rows of the device-resident step, bit for bit
     e2e_same = all(torch.equal(out_h[kk].to(dev), res[kk]) for kk in out_h)
     e2e_ok = torch.tensor([1 if e2e_same else 0], device=dev)
@@ -391,7 +407,8 @@ def bench_multi_gpu(args, cfg_name, cfg, dev, rank, world, ClockSampler, hbm_pea
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": L / e2e_ms / 1e6, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "note": "per-rank bytes; max-over-ranks time; every step ships its own inputs and results; the H2D of step "
-                                                   "i+1 overlaps the table exchange + search of step i (single-buffered: the packed stream is dead by then)",
+                                                   "i+1 starts when the H2D of step i is done (%d device buffer(s) for the packed stream: it is dead once "
+                                                   "a step's key partition is built), i.e. it runs beside the table exchange + search of the steps in flight" % n_buf,
                     "rank0_ms_since_step_start": e2e_phases,
                     "box_h2d_ceiling_GBps_all_ranks_copying": h2d_peak,
                     "h2d_floor_ms": h2d * world / h2d_peak / 1e6 if h2d_peak else None},
