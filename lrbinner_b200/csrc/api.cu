@@ -58,11 +58,16 @@ extern "C" void* lrb_pinned_alloc(size_t bytes) {
 extern "C" void lrb_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- context -----------------------------------------------------------------------------------
+// dry run of the reserve() calls of a batch: "do the buffers of earlier calls already hold this batch?" (thread-local: every
+// device plans on its own host thread)
+static thread_local bool t_reserve_dry = false;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return LRB_OK;
+        if (t_reserve_dry) return LRB_ENOMEM;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -673,6 +678,20 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
         CTX_CUDA(cudaSetDevice(p.c->device));
         int rc2;
         if (need_table && (rc2 = p.c->table.reserve(sizeof(uint32_t) * (size_t)kTableEntries))) return rc2;
+        const uint64_t b0 = r->read_blk[p.r0], b1 = r->read_blk[p.r1];
+        const uint64_t t0 = (uint64_t)(std::lower_bound(r->tile_read, r->tile_read + r->n_tiles, (uint32_t)p.r0) - r->tile_read);
+        const uint64_t t1 = (uint64_t)(std::lower_bound(r->tile_read, r->tile_read + r->n_tiles, (uint32_t)p.r1) - r->tile_read);
+        const long long cap_bases = atoll(getenv("LRB_BATCH_BASES") ? getenv("LRB_BATCH_BASES") : "0");   // tests: force small batches
+        if (cap_bases <= 0) {
+            // steady state (a context profiling read sets of one size again and again): the buffers of the previous call hold
+            // this device's whole share -> one batch, and no cudaMemGetInfo (it costs up to ~10 ms beside a busy allocator)
+            lrb_reads shape;
+            shape.n_reads = p.r1 - p.r0; shape.n_blocks = b1 - b0; shape.n_tiles = t1 - t0; shape.n_exc = r->n_exc;
+            t_reserve_dry = true;
+            const int fits = reserve_batch(p.c, &shape, J, J.do_count);
+            t_reserve_dry = false;
+            if (fits == LRB_OK) { p.batches.push_back({p.r0, p.r1}); return LRB_OK; }
+        }
         size_t free_b = 0, total_b = 0;
         CTX_CUDA(cudaMemGetInfo(&free_b, &total_b));
         uint64_t avail = free_b;
@@ -681,12 +700,8 @@ extern "C" int lrb_profile_host(lrb_ctx* c, const lrb_reads* r, int k, long bin_
             avail += b->cap;   // cached buffers of earlier calls are re-used or released by reserve()
         if (multi) avail = avail > (2ull << 30) / 4 ? avail - (2ull << 30) / 4 : 0;   // exchange staging
         const uint64_t budget = (uint64_t)((double)avail * 0.92);
-        const uint64_t b0 = r->read_blk[p.r0], b1 = r->read_blk[p.r1];
-        const uint64_t t0 = (uint64_t)(std::lower_bound(r->tile_read, r->tile_read + r->n_tiles, (uint32_t)p.r0) - r->tile_read);
-        const uint64_t t1 = (uint64_t)(std::lower_bound(r->tile_read, r->tile_read + r->n_tiles, (uint32_t)p.r1) - r->tile_read);
         const uint64_t need = batch_bytes(J, b1 - b0, p.r1 - p.r0, t1 - t0);
         uint64_t nbat = std::max<uint64_t>(1, (need + budget - 1) / std::max<uint64_t>(budget, 1));
-        const long long cap_bases = atoll(getenv("LRB_BATCH_BASES") ? getenv("LRB_BATCH_BASES") : "0");   // tests: force small batches
         if (cap_bases > 0) nbat = std::max<uint64_t>(nbat, ((b1 - b0) * 32 + (uint64_t)cap_bases - 1) / (uint64_t)cap_bases);
         nbat = std::min<uint64_t>(nbat, std::max<uint64_t>(1, p.r1 - p.r0));
         uint64_t lo = p.r0;

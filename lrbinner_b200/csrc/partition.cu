@@ -17,8 +17,8 @@
 // least one block), so the read delta needs 8 bits and shift <= 25.
 //
 //   k_step_hist     one scan of the chunk: windows per (step, bucket) -> step_cnt (u16), per-group totals
-//   k_group_scan    per bucket: exclusive scan of the group totals, bucket total
-//   k_chunk_scan    region offsets of the chunk (exclusive scan over buckets), capacity guard
+//   k_group_scan    per bucket: exclusive scan of the group totals, bucket total; its last CTA also computes the region
+//                   offsets of the chunk (exclusive scan over buckets) and guards the capacity
 //   k_partition     second scan: each CTA walks the steps of its group in order; the entries of a step are ranked
 //                   and placed in shared memory in ONE pass (the staging offsets are known from step_cnt), then
 //                   copied out run by run (contiguous on both sides); writes step_off[bucket][step]
@@ -64,6 +64,7 @@ struct PartMeta {
     uint32_t overflow2[kMaxBuckets];       // second level: bucket b could not be listed (spill area full) -> k_count_keys counts b
     ull spill_n;                           // entries in the spill area (second level: rows / segments that overflowed)
     ull spill_dropped;                     // != 0: the spill area itself overflowed (its buckets are flagged in overflow2)
+    uint32_t scan_ticket;                  // k_group_scan: CTAs that have finished their bucket (the last one scans the chunk)
 };
 static_assert(sizeof(PartMeta) <= sizeof(ull) * LRB_PART_SMALL_U64, "lrb_partition.small too small");
 
@@ -174,8 +175,13 @@ k_step_hist(const uint32_t* __restrict__ codes, const uint32_t* __restrict__ val
     if (tid < kMaxBuckets) T.grp_tot[(size_t)blockIdx.x * kMaxBuckets + tid] = run;
 }
 
-// CTA b: grp_off[g][b] = exclusive scan over groups of grp_tot[g][b]; counts[c][b] = total
-__global__ void __launch_bounds__(256) k_group_scan(StepTables T, uint32_t n_groups, PartMeta* __restrict__ meta, int c) {
+__device__ void chunk_scan_warp(PartMeta* __restrict__ m, int c, int nb, ull capacity);
+
+// CTA b: grp_off[g][b] = exclusive scan over groups of grp_tot[g][b]; counts[c][b] = total.  The CTA that finishes last
+// also computes the chunk's region offsets (chunk_scan_warp): a second launch for that one warp cost 30 us per chunk in the
+// dependency chain of the host pipeline's 16 chunks.
+__global__ void __launch_bounds__(256) k_group_scan(StepTables T, uint32_t n_groups, PartMeta* __restrict__ meta, int c, int nb, ull capacity) {
+    __shared__ uint32_t s_last;
     __shared__ ull s_part[256];
     const uint32_t b = blockIdx.x, tid = threadIdx.x;
     const uint32_t span = (n_groups + 255u) / 256u;
@@ -195,12 +201,23 @@ __global__ void __launch_bounds__(256) k_group_scan(StepTables T, uint32_t n_gro
         T.grp_off[(size_t)g * kMaxBuckets + b] = (uint32_t)acc;  // < 2^31: a chunk has at most 2^31 slots
         acc += T.grp_tot[(size_t)g * kMaxBuckets + b];
     }
-    if (tid == 255) meta->counts[c][b] = s_part[255];
+    if (tid == 255) {
+        meta->counts[c][b] = s_part[255];
+        __threadfence();
+        const uint32_t ticket = atomicAdd(&meta->scan_ticket, 1u);
+        s_last = (ticket == gridDim.x - 1u) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();   // the other CTAs' counts are visible
+        chunk_scan_warp(meta, c, nb, capacity);
+        if (tid == 0) meta->scan_ticket = 0;   // for the next chunk
+    }
 }
 
 // one warp: offsets of chunk c = chunk_base[c] + exclusive scan of its bucket counts; guards the capacity
-__global__ void k_chunk_scan(PartMeta* __restrict__ m, int c, int nb, ull capacity) {
-    const int lane = threadIdx.x;
+__device__ void chunk_scan_warp(PartMeta* __restrict__ m, int c, int nb, ull capacity) {
+    const int lane = threadIdx.x & 31;
     const ull c0 = (lane < nb) ? m->counts[c][lane] : 0ull;
     const ull c1 = (lane + 32 < nb) ? m->counts[c][lane + 32] : 0ull;
     ull x0 = c0, x1 = c1;
@@ -1202,8 +1219,7 @@ static int add_chunk(const lrb_reads_view* dev, const uint32_t* blk_read, uint64
         LRB_LAUNCH("k_step_hist", st, k_step_hist<true><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T));
     else
         LRB_LAUNCH("k_step_hist", st, k_step_hist<false><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, shift, n_steps, G, step0, T));
-    LRB_LAUNCH("k_group_scan", st, k_group_scan<<<nb, 256, 0, st>>>(T, n_groups, meta, c));
-    LRB_LAUNCH("k_chunk_scan", st, k_chunk_scan<<<1, 32, 0, st>>>(meta, c, nb, (ull)part->capacity));
+    LRB_LAUNCH("k_group_scan", st, k_group_scan<<<nb, 256, 0, st>>>(T, n_groups, meta, c, nb, (ull)part->capacity));
 #define LRB_LAUNCH_PART(RID, FULLK, ...)                                                                                              \
     LRB_LAUNCH("k_partition", st, k_partition<RID, FULLK, ##__VA_ARGS__><<<n_groups, kPartThreads, 0, st>>>(dev->codes, dev->valid, br, blk_lo, blk_hi, part->key_lo, part->key_hi, \
                                                                shift, nb, n_steps, G, step0, T, meta, c, part->keys))
