@@ -47,6 +47,11 @@ static inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && 
 struct Parsed {
     std::string pool;  // sequences that span several lines, concatenated (single-line ones stay in the file image)
     std::vector<Record> recs;
+    // streaming (gzip) mode: where every record's header starts, and where the record begins that was being parsed when the
+    // data ran out (== n when none was): the reader keeps everything from there on for the next round
+    bool want_hdr = false;
+    std::vector<uint64_t> hdr;
+    size_t open_hdr = 0;
 };
 
 // Parses the records whose header character lies in [pos, limit).  `pos` is either 0 (the start of the stream) or
@@ -58,6 +63,7 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
     std::string qual;
     bool reserved = false;
     *ended = false;
+    out.open_hdr = n;
     while (true) {
         size_t hdr;
         if (!pending) {
@@ -69,6 +75,7 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
             hdr = pos - 1;
         }
         if (hdr >= limit) return hdr;
+        out.open_hdr = hdr;   // the record being parsed from here on is complete only once the next header (or EOF) is seen
         if (pos >= n) { *ended = true; return n; }  // nothing after the header char
         // name
         size_t i = pos;
@@ -147,6 +154,7 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
         }
         if (seq_len > 0xFFFFFFFFull) { out.pool.resize(pool_off); *ended = true; return n; }  // > 4 Gbase record: not representable
         out.recs.push_back(Record{multi ? (uint64_t)pool_off : (uint64_t)first_off, (uint32_t)seq_len, multi ? 1u : 0u});
+        if (out.want_hdr) out.hdr.push_back(hdr);
     }
 }
 
