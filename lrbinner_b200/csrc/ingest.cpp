@@ -52,6 +52,8 @@ struct Parsed {
     bool want_hdr = false;
     std::vector<uint64_t> hdr;
     size_t open_hdr = 0;
+    bool tail_open = false;    // the last record's parse ran into the end of the data (it may continue in the next chunk)
+    bool end_touched = false;  // the stream "ended" because the data ran out, not because of a malformed record
 };
 
 // Parses the records whose header character lies in [pos, limit).  `pos` is either 0 (the start of the stream) or
@@ -68,7 +70,7 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
         size_t hdr;
         if (!pending) {
             while (pos < n && buf[pos] != '>' && buf[pos] != '@') ++pos;
-            if (pos >= n) { *ended = true; return n; }
+            if (pos >= n) { *ended = true; out.end_touched = true; return n; }
             hdr = pos;
             pending = buf[pos++];
         } else {
@@ -76,14 +78,16 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
         }
         if (hdr >= limit) return hdr;
         out.open_hdr = hdr;   // the record being parsed from here on is complete only once the next header (or EOF) is seen
-        if (pos >= n) { *ended = true; return n; }  // nothing after the header char
+        if (pos >= n) { *ended = true; out.end_touched = true; return n; }  // nothing after the header char
+        bool touched = false;  // some step of this record's parse ran into the end of the data
         // name
         size_t i = pos;
         while (i < n && !is_space(buf[i])) ++i;
         int delim = 0;
-        if (i < n) { delim = buf[i]; pos = i + 1; } else pos = n;
+        if (i < n) { delim = buf[i]; pos = i + 1; } else { pos = n; touched = true; }
         if (delim != '\n') {  // comment to end of line
             const void* nl = pos < n ? memchr(buf + pos, '\n', n - pos) : nullptr;
+            if (!nl) touched = true;
             pos = nl ? (size_t)((const unsigned char*)nl - buf) + 1 : n;
         }
         // sequence: the first line stays where it is; a second line moves the record into the pool
@@ -92,7 +96,7 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
         bool multi = false;
         int c = -1;
         while (true) {
-            if (pos >= n) { c = -1; break; }
+            if (pos >= n) { c = -1; touched = true; break; }
             c = buf[pos++];
             if (c == '>' || c == '+' || c == '@') break;
             if (c == '\n') continue;
@@ -100,8 +104,11 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
             size_t le = pos;
             if (pos < n) {
                 const void* nl = memchr(buf + pos, '\n', n - pos);
+                if (!nl) touched = true;
                 le = nl ? (size_t)((const unsigned char*)nl - buf) : n;
                 pos = nl ? le + 1 : n;
+            } else {
+                touched = true;
             }
             // kseq appends the first char, then the rest of the line, then drops one trailing CR if more than one byte
             // has been accumulated — except when the line was cut by end of data right after its first char
@@ -129,19 +136,22 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
         size_t seq_len = acc;
         if (c == '+') {
             const void* nl = pos < n ? memchr(buf + pos, '\n', n - pos) : nullptr;
-            if (!nl) { out.pool.resize(pool_off); *ended = true; return n; }  // no quality block: stream ends, record dropped
+            if (!nl) { out.pool.resize(pool_off); *ended = true; out.end_touched = true; return n; }  // no quality block: stream ends, record dropped
             pos = (size_t)((const unsigned char*)nl - buf) + 1;
             qual.clear();
             while (pos < n) {
                 const void* q = memchr(buf + pos, '\n', n - pos);
+                if (!q) touched = true;
                 const size_t e = q ? (size_t)((const unsigned char*)q - buf) : n;
                 qual.append((const char*)buf + pos, e - pos);
                 pos = q ? e + 1 : n;
                 if (qual.size() > 1 && qual.back() == '\r') qual.pop_back();
                 if (!(qual.size() < seq_len)) break;
             }
+            if (pos >= n) touched = true;   // the data ran out inside (or right behind) the quality block: kseq reads at least one
+                                            // quality line when there is one, and goes on while the block is shorter than the sequence
             pending = 0;
-            if (qual.size() != seq_len) { out.pool.resize(pool_off); *ended = true; return n; }
+            if (qual.size() != seq_len) { out.pool.resize(pool_off); *ended = true; out.end_touched = touched; return n; }
         }
         // C-string copy: cut at the first NUL
         const unsigned char* sp = multi ? (const unsigned char*)out.pool.data() + pool_off : buf + first_off;
@@ -155,6 +165,8 @@ static size_t parse_range(const unsigned char* buf, size_t n, size_t pos, size_t
         if (seq_len > 0xFFFFFFFFull) { out.pool.resize(pool_off); *ended = true; return n; }  // > 4 Gbase record: not representable
         out.recs.push_back(Record{multi ? (uint64_t)pool_off : (uint64_t)first_off, (uint32_t)seq_len, multi ? 1u : 0u});
         if (out.want_hdr) out.hdr.push_back(hdr);
+        if (touched) out.tail_open = true;
+        if (!pending) out.open_hdr = pos;   // a complete FASTQ record: whatever follows starts here
     }
 }
 
@@ -182,13 +194,18 @@ static size_t find_candidate(const unsigned char* buf, size_t n, size_t from) {
 // Whole-stream parse on `threads` threads: ranges start at guessed record boundaries and are parsed speculatively;
 // a sequential pass then keeps a range's result only if the preceding range really ended on its start, and
 // re-parses it from the true boundary otherwise.  The outcome equals parse_range(0, n) by construction.
-static void parse_all(const unsigned char* buf, size_t n, int threads, size_t min_chunk, std::vector<Parsed>& parts) {
+// *stream_ended (optional): the stream ended for good inside this buffer (parts.back() says whether because the data ran out)
+static void parse_all(const unsigned char* buf, size_t n, int threads, size_t min_chunk, std::vector<Parsed>& parts,
+                      bool want_hdr = false, bool* stream_ended = nullptr) {
     parts.clear();
     size_t nr = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n / std::max<size_t>(min_chunk, 1)));
+    if (stream_ended) *stream_ended = false;
     if (nr == 1) {
         parts.resize(1);
+        parts[0].want_hdr = want_hdr;
         bool ended;
         parse_range(buf, n, 0, n, parts[0], &ended);
+        if (stream_ended) *stream_ended = ended;
         return;
     }
     std::vector<size_t> start(nr + 1);
@@ -196,6 +213,7 @@ static void parse_all(const unsigned char* buf, size_t n, int threads, size_t mi
     for (size_t t = 1; t < nr; ++t) start[t] = std::max(start[t - 1], find_candidate(buf, n, n / nr * t));
     start[nr] = n;
     std::vector<Parsed> spec(nr);
+    for (auto& sp : spec) sp.want_hdr = want_hdr;
     std::vector<size_t> next(nr);
     std::vector<char> ended(nr);
     {
@@ -220,12 +238,14 @@ static void parse_all(const unsigned char* buf, size_t n, int threads, size_t mi
             parts.push_back(std::move(spec[t]));
         } else {                                   // the guess was not a record boundary: parse from the real one
             Parsed fix;
+            fix.want_hdr = want_hdr;
             bool e = false;
             cur = parse_range(buf, n, cur, start[t + 1], fix, &e);
             done = e;
             parts.push_back(std::move(fix));
         }
     }
+    if (stream_ended) *stream_ended = done;
 }
 
 // The decompressed file image: a private mapping for plain files, a heap buffer for gzip (zlib's gzread, like
@@ -395,7 +415,7 @@ static bool pin_reads_default() {
     return e && atoi(e) > 0;
 }
 
-static int build_layout(lrb_reads* r, bool zero = false, bool want_pinned = true) {
+static int build_layout(lrb_reads* r, bool zero = false, bool want_pinned = true, bool alloc_stream = true) {
     const uint64_t n = r->n_reads;
     r->read_blk = (uint32_t*)malloc(sizeof(uint32_t) * (n + 1));
     if (!r->read_blk) return lrb_set_error(LRB_ENOMEM, "out of memory (read_blk)");
@@ -422,6 +442,11 @@ static int build_layout(lrb_reads* r, bool zero = false, bool want_pinned = true
             r->tile_blk[t] = b;
             ++t;
         }
+    }
+    if (!alloc_stream) {   // the caller packed while reading (streamed gzip): codes / valid are in place and large enough
+        r->codes[2 * blk] = r->codes[2 * blk + 1] = 0;
+        r->valid[blk] = 0;
+        return LRB_OK;
     }
     r->codes = (uint32_t*)lrb_host_alloc(sizeof(uint32_t) * (2 * blk + 2), &r->pinned, want_pinned);
     bool pinned2 = r->pinned;
@@ -523,6 +548,135 @@ static int index_valid(lrb_reads* r, int threads) {
 
 }  // namespace
 
+// ---- gzip input, streamed ------------------------------------------------------------------------------------------
+// A gzip stream cannot be split, but it need not be inflated as a whole either (round 1 did: a 100 Gbase .gz needed 100 GB
+// of RAM).  The file is inflated in chunks by a producer thread while the previous chunk is parsed (all `threads`
+// ranges) and packed; a record whose parse ran into the end of the data available so far is kept back, with everything
+// after it, for the next round.  Host memory: the packed stream (0.375 B/base) + two chunks + one record.
+// Record semantics are parse_range's, so the result equals the whole-image parse (tests: every fixture and the fuzz
+// files, gzip-compressed, with chunks of 1 .. 4096 bytes, against the oracle reader).
+namespace {
+
+struct GrowWords {
+    uint32_t* p = nullptr;
+    size_t cap = 0;  // words
+    bool need(size_t words) {
+        if (words <= cap) return true;
+        size_t nc = std::max<size_t>(std::max<size_t>(words, cap + cap / 2), 1u << 16);
+        void* q = realloc(p, nc * sizeof(uint32_t));
+        if (!q) return false;
+        p = (uint32_t*)q;
+        cap = nc;
+        return true;
+    }
+};
+
+int reads_from_gz_stream(const char* path, int threads, lrb_reads** out) {
+    gzFile f = gzopen(path, "rb");
+    if (!f) { *out = new lrb_reads(); return build_layout(*out, true, false); }   // unreadable == empty stream, like the tools
+    gzbuffer(f, 1 << 20);
+    size_t chunk = 64u << 20;   // measured (200 MB FASTA, 8 threads): 64 MiB chunks 1.16 s, one 256 MiB chunk 1.52 s, whole image 1.19 s
+    {
+        const char* e = getenv("LRB_GZ_CHUNK");   // tests: chunks of a few bytes
+        if (e && atoll(e) > 0) chunk = (size_t)atoll(e);
+    }
+    size_t min_chunk = 8u << 20;
+    {
+        const char* e = getenv("LRB_PARSE_CHUNK");
+        if (e && atoll(e) > 0) min_chunk = (size_t)atoll(e);
+    }
+    threads = std::max(1, std::min(threads, 64));
+    std::vector<unsigned char> work, next(chunk);
+    size_t next_n = 0;
+    bool next_eof = false;
+    auto inflate = [&]() {   // fills `next`; short read == end of the stream (or a damaged one: the tools stop quietly there too)
+        next_n = 0;
+        next_eof = false;
+        while (next_n < chunk) {
+            const int got = gzread(f, next.data() + next_n, (unsigned)std::min<size_t>(chunk - next_n, 1u << 30));
+            if (got <= 0) { next_eof = true; break; }
+            next_n += (size_t)got;
+        }
+    };
+    std::vector<uint32_t> lens;
+    GrowWords codes, valid;
+    uint64_t blk = 0;
+    int rc = LRB_OK;
+    inflate();
+    bool eof = false;
+    struct Item { const unsigned char* s; uint32_t len; uint64_t blk; };
+    std::vector<Item> items;
+    std::vector<Parsed> parts;
+    while (!eof && rc == LRB_OK) {
+        work.insert(work.end(), next.begin(), next.begin() + (ptrdiff_t)next_n);
+        eof = next_eof;
+        std::thread producer;
+        if (!eof) producer = std::thread(inflate);   // the next chunk inflates while this one is parsed and packed
+        bool ended = false;
+        parse_all(work.data(), work.size(), threads, min_chunk, parts, true, &ended);
+        size_t carry_from = work.size();
+        bool stop = false;
+        if (!eof) {
+            Parsed& last = parts.back();
+            if (ended && !last.end_touched) stop = true;            // a malformed record ends the stream for good (kseq.h:209-214)
+            else if (last.tail_open && !last.recs.empty()) {        // the last record may go on in the next chunk: parse it again then
+                carry_from = (size_t)last.hdr.back();
+                last.recs.pop_back();
+                last.hdr.pop_back();
+            } else carry_from = last.open_hdr;
+        }
+        items.clear();
+        for (auto& p : parts)
+            for (const Record& rec : p.recs) {
+                items.push_back({rec.in_pool ? (const unsigned char*)p.pool.data() + rec.off : work.data() + rec.off, rec.len, blk});
+                blk += (uint64_t)rec.len / 32 + 1;
+                lens.push_back(rec.len);
+            }
+        if (blk > 0xFFFFFFF0ull) rc = lrb_set_error(LRB_EINVAL, "read set too large: more than 2^32 blocks (137 Gbases)");
+        else if (!codes.need(2 * blk + 2) || !valid.need(blk + 1)) rc = lrb_set_error(LRB_ENOMEM, "out of memory (packed stream, %llu blocks)", (unsigned long long)blk);
+        if (rc == LRB_OK && !items.empty()) {
+            const int T = items.size() < 64 ? 1 : threads;
+            auto work_fn = [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i) pack_read(items[i].s, items[i].len, codes.p + 2 * items[i].blk, valid.p + items[i].blk);
+            };
+            if (T == 1) work_fn(0, items.size());
+            else {
+                std::vector<std::thread> pool;
+                const uint64_t b_lo = items.front().blk, b_span = blk - b_lo;
+                size_t lo = 0;
+                for (int t = 0; t < T; ++t) {
+                    size_t hi = items.size();
+                    if (t + 1 < T) {
+                        const uint64_t target = b_lo + b_span * (uint64_t)(t + 1) / (uint64_t)T;
+                        hi = (size_t)(std::lower_bound(items.begin() + (ptrdiff_t)lo, items.end(), target, [](const Item& it, uint64_t v) { return it.blk < v; }) - items.begin());
+                    }
+                    pool.emplace_back(work_fn, lo, hi);
+                    lo = hi;
+                }
+                for (auto& th : pool) th.join();
+            }
+        }
+        if (producer.joinable()) producer.join();
+        if (stop) break;
+        if (!eof) work.erase(work.begin(), work.begin() + (ptrdiff_t)carry_from);
+    }
+    gzclose(f);
+    if (rc) { free(codes.p); free(valid.p); return rc; }
+    lrb_reads* r = new lrb_reads();
+    r->n_reads = lens.size();
+    r->read_len = (uint32_t*)malloc(sizeof(uint32_t) * (lens.size() + 1));
+    if (!r->read_len || !codes.need(2 * blk + 2) || !valid.need(blk + 1)) { free(codes.p); free(valid.p); free_reads(r); return lrb_set_error(LRB_ENOMEM, "out of memory (read_len)"); }
+    if (!lens.empty()) memcpy(r->read_len, lens.data(), sizeof(uint32_t) * lens.size());
+    r->codes = codes.p;
+    r->valid = valid.p;
+    r->pinned = false;
+    if ((rc = build_layout(r, false, false, /*alloc_stream=*/false)) || (rc = index_valid(r, threads))) { free_reads(r); return rc; }
+    *out = r;
+    return LRB_OK;
+}
+
+}  // namespace
+
 extern "C" int lrb_reads_index_valid(lrb_reads* r, int threads, uint64_t* n_exceptions) {
     if (!r) return lrb_set_error(LRB_EINVAL, "lrb_reads_index_valid: null argument");
     const int rc = index_valid(r, threads);
@@ -544,6 +698,14 @@ extern "C" int lrb_reads_from_file(const char* path, int threads, lrb_reads** ou
     const bool trace = getenv("LRB_INGEST_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
+    {   // gzip input: streamed (bounded host memory, inflate beside parse) unless LRB_GZ_WHOLE=1 asks for the whole image
+        unsigned char magic[2] = {0, 0};
+        const int fd = open(path, O_RDONLY);
+        const bool gz = fd >= 0 && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (fd >= 0) close(fd);
+        const char* whole = getenv("LRB_GZ_WHOLE");
+        if (gz && !(whole && atoi(whole) > 0)) return reads_from_gz_stream(path, threads, out);
+    }
     FileImage img;
     load_file(path, img);
     const double t1 = now();

@@ -176,6 +176,70 @@ def test_parallel_parse_of_structured_files(tmp_path):
                 assert pr.unpack(i) == bytes(b"ACTG"[(c >> 1) & 3] for c in x), (it, i, threads, chunk)
 
 
+def _load_gz_streamed(path, chunk, threads=3, parse_chunk=None):
+    env = {"LRB_GZ_CHUNK": str(chunk)}
+    if parse_chunk is not None:
+        env["LRB_PARSE_CHUNK"] = str(parse_chunk)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return PackedReads.from_file(str(path), threads=threads)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", golden_inputs())
+def test_streamed_gzip_ingest_equals_the_whole_image_parse(name, tmp_path):
+    """gzip input is inflated chunk by chunk while the previous chunk is parsed; a record cut by the end of a chunk is parsed
+    again with more data.  Chunks of 1 .. 4096 bytes put a chunk boundary at every byte of every fixture."""
+    src = os.path.join(GOLDEN, name)
+    raw = _gz(src) if name.endswith(".gz") else open(src, "rb").read()
+    gz = tmp_path / "in.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(raw)
+    seqs, _ = oracle.parse_reads(raw)
+    for chunk, threads, pchunk in ((1, 1, None), (3, 2, 2), (64, 4, 16), (1000, 3, 100), (4096, 8, None), (1 << 28, 4, None)):
+        pr = _load_gz_streamed(gz, chunk, threads, pchunk)
+        assert pr.n_reads == len(seqs) and list(pr.read_len) == [len(x) for x in seqs], (name, chunk)
+        _check_packing(pr, seqs)
+        blk, word = pr.exceptions()
+        want = _default_valid(pr)[:pr.n_blocks]
+        if len(blk):
+            want[blk] = word
+        assert np.array_equal(want, pr.valid[:pr.n_blocks]), (name, chunk)
+
+
+def test_streamed_gzip_ingest_fuzz(tmp_path):
+    """random byte soup (headers, quality-like lines, CR, NUL-free) through the streamed reader with tiny chunks"""
+    rng = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"ACGTacgtN>@+\n\r \t;-", dtype=np.uint8)
+    probs = np.array([8, 8, 8, 8, 1, 1, 1, 1, 1, .6, .6, .6, 4, 1.5, .5, .3, .2, .2])
+    probs /= probs.sum()
+    for it in range(150):
+        n = int(rng.integers(0, 600))
+        data = rng.choice(alphabet, size=n, p=probs).tobytes()
+        if it % 5 == 0:
+            data = b">" + data
+        if it % 7 == 0:
+            data = data.replace(b"+", b"+\n")
+        if it % 3 == 0:      # well-formed FASTQ records in the soup, so that complete quality blocks meet chunk boundaries
+            s = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(1, 40))).tobytes()
+            data = b"@r\n" + s + b"\n+\n" + b"@" * len(s) + b"\n" + data
+        path = tmp_path / f"z{it}.gz"
+        with gzip.open(path, "wb") as f:
+            f.write(data)
+        seqs, _ = oracle.parse_reads(data)
+        for chunk, threads, pchunk in ((1, 1, None), (5, 4, 3), (37, 3, 8)):
+            pr = _load_gz_streamed(path, chunk, threads, pchunk)
+            assert list(pr.read_len) == [len(x) for x in seqs], (it, chunk, data)
+            for i, x in enumerate(seqs):
+                assert pr.unpack(i) == bytes(b"ACTG"[(c >> 1) & 3] for c in x), (it, i, chunk)
+
+
 def test_ingest_nul_byte_and_missing_file(tmp_path):
     p = tmp_path / "nul.fa"
     p.write_bytes(b">a\nACGT\0ACGTACGT\n>b\nGGGG\n")
