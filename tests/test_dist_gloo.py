@@ -157,6 +157,66 @@ def test_two_rank_plans_match_single_process_oracle(plan):
     assert covered == list(range(len(seqs)))
 
 
+def _digest_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    import bench_multi
+    from lrbinner_b200 import dist as lrb_dist
+    from oracle import oracle
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seqs, _ = oracle.load_reads(os.path.join(GOLDEN, "g06_community.fa"))
+    eng = OracleEngine(seqs[:41])
+    out = {}
+    for plan in ("keyshard_ag", "readshard_ar"):       # both leave the whole table on every rank; different collectives
+        res = lrb_dist.profile_distributed(eng, K, BS, BC, plan, pipeline_exchange=False)
+        out[plan] = bench_multi.content_digest(torch, dist, res, BC, res["table"], canon_bit=KT)
+    # what the old mass check could not see: a row on the wrong read, a count in the wrong bin, a lost table update
+    res["hist"] = res["hist"].clone()
+    if rank == 1 and res["hist"].shape[0] > 1:
+        res["hist"][[0, 1]] = res["hist"][[1, 0]]                         # two rows swapped (same totals)
+    out["rows_swapped"] = bench_multi.content_digest(torch, dist, res, BC, res["table"], canon_bit=KT)
+    res["hist"] = res["hist"].clone()
+    if rank == 0:
+        row = int(torch.nonzero(res["hist"].sum(dim=1))[0])
+        col = int(torch.nonzero(res["hist"][row])[0])
+        res["hist"][row, col] -= 1
+        res["hist"][row, (col + 1) % BC] += 1                             # one window in the wrong bin (same totals)
+    out["wrong_bin"] = bench_multi.content_digest(torch, dist, res, BC, res["table"], canon_bit=KT)
+    t = res["table"].clone()
+    nz = torch.nonzero(t.view(-1, 2, 1 << KT)[:, 0, :].reshape(-1))
+    i = int(nz[len(nz) // 2])
+    flat = t.view(-1, 2, 1 << KT)
+    flat[i >> KT, 0, i & ((1 << KT) - 1)] -= 1                             # one lost update in the canonical half
+    out["lost_update"] = {"table": bench_multi.table_digest(torch, t, KT)}
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_verify_digests_agree_across_plans_and_catch_what_totals_cannot():
+    """bench_multi's `verify` digests (position-weighted sums mod 2^64, all-reduced): equal across plans that use
+    different collectives, different as soon as a row moves, a window changes bin or a table update is lost — the
+    failures the round-1 mass check (sum of sums, of hist, of comp) was blind to."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_digest_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    a, b = got[0], got[1]
+    assert a["keyshard_ag"] == a["readshard_ar"] == b["keyshard_ag"] == b["readshard_ar"]
+    ok = a["readshard_ar"]
+    assert a["rows_swapped"]["hist"] != ok["hist"] and a["rows_swapped"]["sums"] == ok["sums"]
+    assert a["wrong_bin"]["hist"] != ok["hist"] and a["wrong_bin"]["hist"] != a["rows_swapped"]["hist"]
+    assert a["lost_update"]["table"] != ok["table"] and b["lost_update"]["table"] != ok["table"]
+
+
 def test_shard_arithmetic():
     from lrbinner_b200 import dist as d
     for n in (0, 1, 7, 8, 41, 1000):
