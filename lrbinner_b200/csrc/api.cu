@@ -397,7 +397,15 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
     const uint64_t n = r->n_reads, nb = r->n_blocks;
     const bool lists = J.use_part && nb > 0 && (J.do_count || (with_rids && J.do_search));
     int rc;
-    if ((rc = reserve_batch(c, r, J, J.do_count))) return rc;
+    if ((rc = reserve_batch(c, r, J, J.do_count))) {
+        // buffers left over from a differently shaped earlier call can add up to more than the device has (the plan counts
+        // them as reusable): give everything back and allocate this batch afresh before calling it an error
+        for (DevBuf* b : {&c->codes, &c->valid, &c->read_len, &c->read_blk, &c->tile_read, &c->tile_blk, &c->comp, &c->hist, &c->sums,
+                          &c->part_keys, &c->part_steps, &c->part_sub, &c->blk_read, &c->exc_blk, &c->exc_valid, &c->text})
+            b->release();
+        cudaGetLastError();
+        if ((rc = reserve_batch(c, r, J, J.do_count))) return rc;
+    }
     const ChunkPlan ch = plan_chunks(r, J.h2d_chunks);
     if (timed) CTX_CUDA(cudaEventRecord(c->ev[0], st));
     else CTX_CUDA(cudaEventRecord(c->sync_ev[LRB_PART_MAX_CHUNKS + 1], st));
