@@ -283,6 +283,14 @@ class PeerExchange:
         prio = -1 if os.environ.get("LRB_XCHG_PRIO", "1") != "0" else 0
         self.comm = torch.cuda.Stream(device=device, priority=prio)
 
+    def timings(self):
+        """Of the last run(), after a synchronize: ms from "count done" to the first round's rows being final on this rank
+        (what the search has to wait for) and to the last round (length of the whole exchange on the copy stream)."""
+        if not getattr(self, "last_events", None):
+            return None
+        ready, first, last = self.last_events
+        return {"first_round_ms": ready.elapsed_time(first), "whole_exchange_ms": ready.elapsed_time(last)}
+
     def run(self, engine, table, bin_size, bins, hist_all, sums_all, lo, hi):
         """table (== self.table) holds this rank's private canonical counts; on return it holds the global, mirrored table
         and hist_all / sums_all the coverage rows of the reads [lo, hi).
@@ -350,17 +358,6 @@ class PeerExchange:
             # slice (single GPU, profiles/r02_exp1_variants.jsonl: search 20.5 -> 26.2 ms with the mirror beside it)
             engine.mirror(table)
 
-
-def _peer_exchange_timings(self):
-    """(ms from count done to the first round's rows being final here = what the search has to wait for,
-        ms from count done to the last round = length of the whole exchange on the copy stream) of the last run()."""
-    if not getattr(self, "last_events", None):
-        return None
-    ready, first, last = self.last_events
-    return {"first_round_ms": ready.elapsed_time(first), "whole_exchange_ms": ready.elapsed_time(last)}
-
-
-PeerExchange.timings = _peer_exchange_timings
 
 _SIDE = {}
 
