@@ -31,7 +31,7 @@ res = {}
 for devices in ([0], list(range(n_gpus))):
     ctx = Context(devices)
     walls = []
-    for i in range(5):
+    for i in range(int(sys.argv[3]) if len(sys.argv) > 3 else 5):
         t0 = time.perf_counter()
         ctx.profile(layout, k=k, bin_size=32, bins=10, out=out)
         walls.append((time.perf_counter() - t0) * 1e3)
