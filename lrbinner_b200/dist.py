@@ -72,6 +72,14 @@ class CudaEngine:
     def zeros(self, shape):
         return self.torch.zeros(shape, dtype=self.torch.int32, device=self.device)
 
+    def zeros_rows(self, shape, lo, hi):
+        """A tensor indexed by GLOBAL read of which only rows [lo, hi) will be written and returned: only those are zeroed
+        (at N = 8 the composition rows of the whole global set are 4.4 GB — 0.7 ms of memset per step for rows no kernel
+        touches; the row sums of foreign reads are computed from uninitialised rows and never looked at)."""
+        t = self.torch.empty(shape, dtype=self.torch.int32, device=self.device)
+        t[lo:hi].zero_()
+        return t
+
     def _blocks(self, lo, hi):
         if self._rb is None:
             self._rb = self.dr.read_blk.cpu().numpy().view(np.uint32)
@@ -410,7 +418,8 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
     # feed (plan X only): [(read_lo_j, read_hi_j, wait_j)] — this rank's reads arrive in chunks; wait_j() orders the
     # current stream after chunk j's arrival.  Composition and the key partition then run chunk by chunk.
     fed = feed is not None and plan == "readshard_ar" and hasattr(engine, "count_fed") and hi > lo
-    comp_all = engine.zeros((n, P))
+    zeros_rows = getattr(engine, "zeros_rows", lambda shape, a, b: engine.zeros(shape))   # rows [lo, hi) zeroed, the rest unspecified
+    comp_all = zeros_rows((n, P), lo, hi)
     if hi > lo and not fed:
         engine.composition(k, comp_all, lo, hi)
     comp = comp_all[lo:hi]
@@ -438,8 +447,8 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
             on_comp(comp)
         bit = getattr(engine, "canon_bit", None)
         if pipelined:
-            hist_all = engine.zeros((n, bins))
-            sums_all = engine.zeros((n,))
+            hist_all = zeros_rows((n, bins), lo, hi)
+            sums_all = zeros_rows((n,), lo, hi)
             if peer_exchange is not None:
                 peer_exchange.run(engine, table, bin_size, bins, hist_all, sums_all, lo, hi)   # leaves the table mirrored
                 mark("exchange_table+search+mirror")
@@ -477,8 +486,8 @@ def profile_distributed(engine, k, bin_size, bins, plan, table=None, group=None,
     else:
         engine.mirror(table)
         mark("mirror")
-        hist_all = engine.zeros((n, bins))
-        sums_all = engine.zeros((n,))
+        hist_all = zeros_rows((n, bins), lo, hi)
+        sums_all = zeros_rows((n,), lo, hi)
         if hi > lo:
             engine.search(table, bin_size, bins, hist_all, sums_all, lo, hi, 0, entries)
         hist, sums = hist_all[lo:hi], sums_all[lo:hi]
