@@ -260,6 +260,11 @@ struct DevPlan {
     std::string err;
 };
 
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
 bool host_ptr_is_pinned(const void* p) {
     if (!p) return true;
     cudaPointerAttributes a;
@@ -418,9 +423,12 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
     // compute stream: zero the outputs while the first chunk is in flight.  The table is zeroed only when counts will be
     // ADDED to it (several batches, or no lists): a device's only batch WRITES its table slices (apply mode bit 3).
     const bool count_writes = J.do_count && lists && only_batch;
+    // experiment (LRB_COMP_BESIDE=1): the composition does not ride along with the chunks but runs on the copy_out stream
+    // beside the search, once the count is enqueued (it needs nothing but the packed stream)
+    const bool comp_beside = J.do_comp && n && only_batch && lists && J.do_count && J.do_search && env_int("LRB_COMP_BESIDE", 0) > 0;
     if (J.do_count && first_batch && !count_writes)
         CTX_CUDA(cudaMemsetAsync(c->table.p, 0, sizeof(uint32_t) * (size_t)kTableEntries, st));
-    if (J.do_comp && n) CTX_CUDA(cudaMemsetAsync(c->comp.p, 0, sizeof(uint32_t) * n * J.P, st));
+    if (J.do_comp && n && !comp_beside) CTX_CUDA(cudaMemsetAsync(c->comp.p, 0, sizeof(uint32_t) * n * J.P, st));
     CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[0], 0));  // index arrays (and validity exceptions) are on the device
     if (!ship_valid && (rc = lrb_dev_fill_valid(&v, (const uint32_t*)c->exc_blk.p, (const uint32_t*)c->exc_valid.p, r->n_exc, st))) return rc;
     if (lists) {
@@ -429,7 +437,7 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
     }
     for (int i = 0; i < ch.n; ++i) {
         CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[1 + i], 0));
-        if (J.do_comp && n && (rc = lrb_dev_composition(&v, J.k, (uint32_t*)c->comp.p, ch.ct[i], ch.ct[i + 1], st))) return rc;
+        if (J.do_comp && n && !comp_beside && (rc = lrb_dev_composition(&v, J.k, (uint32_t*)c->comp.p, ch.ct[i], ch.ct[i + 1], st))) return rc;
         if (lists) {
             if ((rc = lrb_dev_partition_add(&v, (const uint32_t*)c->blk_read.p, ch.cb[i], ch.cb[i + 1], &c->part, st))) return rc;
         } else if (J.do_count && !J.use_part) {
@@ -438,7 +446,7 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
     }
     if (timed) CTX_CUDA(cudaEventRecord(c->ev[2], st));  // composition (+ partition) of every chunk done
     c->comp_late_dst = nullptr;
-    if (J.do_comp && n) {
+    if (J.do_comp && n && !comp_beside) {
         uint32_t* dst = J.comp + (size_t)row0 * J.P;
         const size_t bytes = sizeof(uint32_t) * n * J.P;
         if (defer_comp) {                          // pageable destination: goes home at the end of the call
@@ -456,6 +464,17 @@ int stage_front(lrb_ctx* c, const lrb_reads* r, const Job& J, uint64_t row0, boo
         const int mode = (c->part.sub ? (1 | 4) : 1) | (count_writes ? 8 : 0);
         if ((rc = lrb_dev_partition_apply(&c->part, mode, (uint32_t*)c->table.p, J.bin_size, J.bins, nullptr, nullptr, st))) return rc;
     }
+    if (comp_beside) {
+        uint32_t* dst = J.comp + (size_t)row0 * J.P;
+        const size_t bytes = sizeof(uint32_t) * n * J.P;
+        CTX_CUDA(cudaEventRecord(c->mirrored, st));   // (event free at this point: the mirror comes after the search)
+        CTX_CUDA(cudaStreamWaitEvent(sout, c->mirrored, 0));
+        CTX_CUDA(cudaMemsetAsync(c->comp.p, 0, bytes, sout));
+        if ((rc = lrb_dev_composition(&v, J.k, (uint32_t*)c->comp.p, 0, r->n_tiles, sout))) return rc;
+        if (defer_comp) { c->comp_late_dst = dst; c->comp_late_bytes = bytes; }
+        else CTX_CUDA(cudaMemcpyAsync(dst, c->comp.p, bytes, cudaMemcpyDeviceToHost, sout));
+        CTX_CUDA(cudaEventRecord(c->sync_ev[LRB_PART_MAX_CHUNKS + 1], sout));
+    }
     return LRB_OK;
 }
 
@@ -472,11 +491,11 @@ int rows_home(lrb_ctx* c, const Job& J, uint64_t n, uint64_t row0) {
         CTX_CUDA(cudaMemcpyAsync(J.hist + (size_t)row0 * J.bins, c->hist.p, sizeof(uint32_t) * n * (size_t)J.bins, cudaMemcpyDeviceToHost, st));
         CTX_CUDA(cudaMemcpyAsync(J.sums + row0, c->sums.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     }
+    CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[LRB_PART_MAX_CHUNKS + 1], 0));  // join the copy_out stream (early composition D2H)
     if (c->comp_late_dst) {
         CTX_CUDA(cudaMemcpyAsync(c->comp_late_dst, c->comp.p, c->comp_late_bytes, cudaMemcpyDeviceToHost, st));
         c->comp_late_dst = nullptr;
     }
-    CTX_CUDA(cudaStreamWaitEvent(st, c->sync_ev[LRB_PART_MAX_CHUNKS + 1], 0));  // join the early composition D2H
     return LRB_OK;
 }
 
@@ -611,11 +630,6 @@ int enqueue_exchange(std::vector<DevPlan>& plans, int n_buckets, int shift, bool
         CTX_CUDA(cudaEventRecord(c->xev[1], c->xchg));
     }
     return LRB_OK;
-}
-
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
 }
 
 }  // namespace
